@@ -1,0 +1,133 @@
+/* spe_b200 — C ABI of the B200-native heatmap -> 6-DoF pose stage.
+ *
+ * Drop-in boundary for ONE path of mohsij/spacecraft-pose-estimation.  The
+ * reference has no FFI for this path; its boundary is three Python call sites.  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference root):
+ *
+ *   spe_max_preds_f32        get_max_preds        landmark_regression/lib/core/inference.py:18-46
+ *   spe_decode_f32           get_final_preds      landmark_regression/lib/core/inference.py:49-79
+ *                            (+ transform_preds   landmark_regression/lib/utils/transforms.py:49-110)
+ *   spe_ransac_epnp_f32      the per-frame loop   pose_estimation/export_predicted_poses_real.py:177-204
+ *                            (confidence filter :186-197, cv2.solvePnPRansac :199-201,
+ *                             cv2.Rodrigues :203, cv_rotation_matrix_to_quat :22-57)
+ *   spe_heatmap_to_pose_f32  the two above back to back with no host hop (the reference goes
+ *                            through pred.mat: lib/dataset/PEdataset.py:121-123 ->
+ *                            export_predicted_poses_real.py:172-173)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every data pointer is a DEVICE pointer, C-contiguous;
+ *     `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - the caller owns every buffer; nothing is allocated per call (scratch comes from the
+ *     caller-provided workspace, size from spe_ransac_workspace_bytes)
+ *   - functions enqueue work on `stream` and return without synchronising; they are re-entrant
+ *     and keep no global state; a model handle is immutable after creation and may be shared by
+ *     threads using the same device
+ *   - return value: SPE_OK (0) or a negative spe_status code; never throws across the ABI.
+ *     Per-frame conditions are reported in status[b] (SPE_FRAME_*), not as errors.
+ */
+#ifndef SPE_B200_H
+#define SPE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPE_ABI_VERSION 1
+#define SPE_MAX_LANDMARKS 32 /* inlier masks are 32-bit */
+#define SPE_MAX_HYPOTHESES 4096
+
+typedef enum spe_status {
+  SPE_OK = 0,
+  SPE_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, J > SPE_MAX_LANDMARKS ... */
+  SPE_ERR_CUDA = -2,             /* a CUDA runtime call failed; see spe_last_cuda_error() */
+  SPE_ERR_WORKSPACE = -3,        /* workspace too small or misaligned */
+  SPE_ERR_UNSUPPORTED = -4
+} spe_status;
+
+/* status[b] values written by spe_ransac_epnp_f32 (what cv2 would have done) */
+typedef enum spe_frame_status {
+  SPE_FRAME_OK = 0,
+  SPE_FRAME_TOO_FEW_POINTS = 1, /* n < 4: cv2.solvePnPRansac raises cv2.error */
+  SPE_FRAME_P3P_UNSUPPORTED = 2, /* n == 4: cv2 switches to its P3P kernel (out of scope) */
+  SPE_FRAME_NO_MODEL = 3         /* no hypothesis reached 5 inliers: cv2 returns ret = False */
+} spe_frame_status;
+
+typedef struct spe_model spe_model_t; /* opaque: landmarks, camera, per-n minimal-set tables */
+
+int spe_abi_version(void);
+const char* spe_status_string(int status);
+/* cudaGetErrorString of the last CUDA failure seen by this thread inside the library */
+const char* spe_last_cuda_error(void);
+
+/* ---- decode -------------------------------------------------------------------------------
+ * hm        [B,J,H,W] float32   raw HRNet output
+ * preds     [B,J,2]   float32   (x, y)
+ * maxvals   [B,J]     float32   (the reference's [B,J,1])
+ * argmax    [B,J]     int32     flat index of the maximum (first on ties, first NaN wins); may be NULL
+ */
+int spe_max_preds_f32(const float* hm, int B, int J, int H, int W, float* preds, float* maxvals,
+                      int32_t* argmax, void* stream);
+
+/* center, scale [B,2] float32 (scale[:,1] is ignored, as in the reference); post_process =
+ * config.TEST.POST_PROCESS.  preds are image pixels after the inverse box affine. */
+int spe_decode_f32(const float* hm, int B, int J, int H, int W, const float* center,
+                   const float* scale, int post_process, float* preds, float* maxvals,
+                   int32_t* argmax, void* stream);
+
+/* Same as spe_decode_f32 but writes the pred.mat row layout directly:
+ * kpts [B,J,3] float32 = (x, y, maxval) (lib/core/function.py:392-393). */
+int spe_decode_kpts_f32(const float* hm, int B, int J, int H, int W, const float* center,
+                        const float* scale, int post_process, float* kpts, int32_t* argmax,
+                        void* stream);
+
+/* ---- pose ---------------------------------------------------------------------------------
+ * landmarks [J,3] float64 HOST (metres; rounded to float32 internally exactly like cv2 does),
+ * K[9] row-major float64 HOST, dist[5] = (k1,k2,p1,p2,k3) float64 HOST (NULL = no distortion).
+ * max_hypotheses bounds `hypotheses` of later calls.  Builds the OpenCV-RNG minimal-set tables
+ * for every point count 6..J on the current device. */
+int spe_pnp_model_create(const double* landmarks, int J, const double* K, const double* dist,
+                         int max_hypotheses, spe_model_t** out);
+int spe_pnp_model_destroy(spe_model_t* model);
+int spe_pnp_model_num_landmarks(const spe_model_t* model);
+/* copies the first `count` minimal sets for n points into out[count*5] (HOST), draw order kept */
+int spe_pnp_model_minimal_sets(const spe_model_t* model, int n, int count, int32_t* out);
+
+size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypotheses);
+
+/* kpts        [B,J,3] float32   (x, y, conf) rows as stored in pred.mat
+ * hypotheses  number of minimal sets scored per frame (cv2's iterationsCount capped to what the
+ *             GPU evaluates; selection replays cv2's sequential adaptive termination)
+ * reproj_err  15.0 in the reference; confidence 0.99 (cv2 default)
+ * conf_floor  a landmark takes part iff conf > conf_floor; pass a negative value to run the
+ *             reference's adaptive 0.95*0.8^k filter per frame (export_predicted_poses_real.py:186-197)
+ * pose7       [B,7] float32 = (qw,qx,qy,qz,tx,ty,tz)
+ * inlier_mask [B] uint32 over the J landmarks (bit j); status [B] int32 (spe_frame_status)
+ * winner_hyp  [B] int32 index of the accepted hypothesis (-1 none); may be NULL
+ * rt          [B,12] float64 = row-major R (9) then t (3) of the final refit; may be NULL
+ */
+int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
+                        float reproj_err, double confidence, float conf_floor, float* pose7,
+                        uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Per-hypothesis scores of the most recent spe_ransac_epnp_f32 call on this workspace, for the
+ * parity tests: counts [B,hypotheses] uint8-as-int32 and masks [B,hypotheses] uint32 (DEVICE). */
+int spe_ransac_debug_scores(const void* workspace, int B, int hypotheses, int32_t* counts,
+                            uint32_t* masks, void* stream);
+
+/* decode + pose with the keypoints kept in HBM; kpts_out [B,J,3] may be NULL only if workspace
+ * has room (it always does: spe_pipeline_workspace_bytes accounts for it). */
+size_t spe_pipeline_workspace_bytes(const spe_model_t* model, int B, int J, int hypotheses);
+int spe_heatmap_to_pose_f32(const spe_model_t* model, const float* hm, int B, int J, int H, int W,
+                            const float* center, const float* scale, int post_process,
+                            int hypotheses, float reproj_err, double confidence, float conf_floor,
+                            float* pose7, uint32_t* inlier_mask, int32_t* status, float* kpts_out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPE_B200_H */

@@ -1,0 +1,391 @@
+// Heatmap decode for sm_100a: argmax + quarter-pixel refine + inverse box affine.
+//
+// Replaces get_max_preds / get_final_preds / transform_preds of the reference
+// (landmark_regression/lib/core/inference.py:18-79, lib/utils/transforms.py:49-110); exact
+// semantics are restated in SURVEY.md App. A and checked against the reference's own outputs in
+// tests/test_decode_gpu.py.
+//
+// HBM-bound: one streaming read of B*J*H*W floats, O(1) flop per byte.  Design:
+//   * persistent CTAs (one per SM), one warp per (frame, landmark) heatmap, maps dealt
+//     round-robin to warps so the chip walks HBM as one moving window
+//   * every warp owns a ring of shared-memory stages filled by bulk async copies
+//     (cp.async.bulk global->shared, SASS UBLKCP) that complete on an mbarrier; lane 0 is the
+//     producer, the whole warp is the consumer, so there is no CTA-wide barrier in the loop and
+//     the bytes in flight per SM (warps x stages x chunk) do not depend on register pressure
+//   * the consumer reads its stage with conflict-free 128-bit shared loads into four independent
+//     (max, first-index) accumulators per lane; the warp-wide result takes two REDUX instructions
+//   * maps that fit one stage take their refinement neighbours from shared memory, longer maps
+//     read the four neighbours back from L2
+//   * the per-map epilogue (index -> x/y, mask, refine, FP64 inverse affine, stores) is batched:
+//     results are parked in shared memory and finished 32 maps at a time, one map per lane
+//   * a plain coalesced-load kernel covers shapes whose maps are not 16-byte aligned
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+
+#include "decode.cuh"
+
+namespace spe {
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNoIndex = 0x7fffffff;
+
+// ------------------------------------------------------------------------------------------
+// (value, first index) bookkeeping with NumPy's argmax semantics: strict > keeps the first
+// maximum, +-0 compare equal, NaN is sticky in the value (max.NaN) and resolved afterwards.
+struct Best {
+  float v;
+  int i;
+};
+
+__device__ __forceinline__ float max_nan(float a, float b) {
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+}
+
+__device__ __forceinline__ void take(Best& b, float x, int idx) {
+  b.i = (x > b.v) ? idx : b.i;  // ordered compare: false as soon as a NaN is involved
+  b.v = max_nan(b.v, x);
+}
+
+__device__ __forceinline__ void merge(Best& a, float v, int i) {
+  // a and (v, i) are both "first maximum of a subset": larger value wins, ties -> lower index
+  const bool better = (v > a.v) | ((v == a.v) & (i < a.i));
+  a.i = better ? i : a.i;
+  a.v = max_nan(a.v, v);
+}
+
+// Warp-wide (max, first index) with two REDUX instructions.  Floats are mapped to unsigned keys
+// that sort like the values (-0 folded into +0 so that +-0 tie on index, as in NumPy).  A NaN
+// anywhere makes the result NaN; its index is resolved by first_nan_index().
+__device__ __forceinline__ Best warp_merge(Best b) {
+  const bool any_nan = __any_sync(kFull, b.v != b.v);
+  const unsigned u = __float_as_uint(b.v + 0.0f);
+  const unsigned key = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  const unsigned kmax = __reduce_max_sync(kFull, key);
+  const int imin = __reduce_min_sync(kFull, key == kmax ? b.i : kNoIndex);
+  const unsigned back = (kmax & 0x80000000u) ? (kmax & 0x7fffffffu) : ~kmax;
+  return Best{any_nan ? __int_as_float(0x7fc00000) : __uint_as_float(back), imin};
+}
+
+// first NaN of a map (only reached when the maximum is NaN)
+__device__ __noinline__ int first_nan_index(const float* __restrict__ map, int hw, int lane) {
+  for (int base = 0; base < hw; base += 32) {
+    const int e = base + lane;
+    const bool is_nan = (e < hw) && (map[e] != map[e]);
+    const unsigned m = __ballot_sync(kFull, is_nan);
+    if (m) return base + __ffs(m) - 1;
+  }
+  return 0;
+}
+
+__device__ __forceinline__ float quarter_sign(float d) {
+  // 0.25 * np.sign(d): sign(0) = 0, sign(NaN) = NaN
+  return d > 0.f ? 0.25f : (d < 0.f ? -0.25f : d);
+}
+
+// One map's epilogue, executed by ONE lane: mask, refine, inverse affine, stores.
+// nb = (left, right, up, down) neighbours of the maximum (only read when the refine applies).
+template <typename NeighbourFn>
+__device__ __forceinline__ void finish_map(const DecodeArgs& a, int map, float v, int idx, NeighbourFn nb) {
+  const int py = idx / a.W, px = idx - py * a.W;
+  float x = 0.f, y = 0.f;
+  if (v > 0.f) {  // inference.py:42-45 (false for NaN)
+    x = (float)px;
+    y = (float)py;
+    if (a.post_process && px > 1 && px < a.W - 1 && py > 1 && py < a.H - 1) {  // inference.py:62
+      float l, r, u, d;
+      nb(l, r, u, d);
+      x += quarter_sign(__fsub_rn(r, l));
+      y += quarter_sign(__fsub_rn(d, u));
+    }
+  }
+  if (a.center != nullptr) {
+    // Inverse box affine, replaying the float32 roundings of get_affine_transform
+    // (transforms.py:65-85).  scale[:,1] never enters.
+    const int f = map / a.J;
+    const float2 c = __ldg(reinterpret_cast<const float2*>(a.center) + f);
+    const float sw = __fmul_rn(__ldg(a.scale + 2 * f), 200.0f);
+    const float q1y = __fsub_rn(c.y, __fmul_rn(sw, 0.5f));
+    const float dd = __fsub_rn(c.y, q1y);
+    const float q2x = __fsub_rn(c.x, dd);
+    const double half_w = 0.5 * (double)a.W, half_h = 0.5 * (double)a.H;
+    const double ax = __ddiv_rn(__dsub_rn((double)c.x, (double)q2x), half_w);
+    const double ay = __ddiv_rn(__dsub_rn((double)c.y, (double)q1y), half_w);
+    const double bx = __dsub_rn((double)c.x, __dmul_rn(ax, half_w));
+    const double by = __dsub_rn((double)c.y, __dmul_rn(ay, half_h));
+    x = (float)__dadd_rn(__dmul_rn(ax, (double)x), bx);
+    y = (float)__dadd_rn(__dmul_rn(ay, (double)y), by);
+  }
+  if (a.kpts != nullptr) {
+    float* o = a.kpts + 3 * (size_t)map;
+    o[0] = x;
+    o[1] = y;
+    o[2] = v;
+  } else {
+    *reinterpret_cast<float2*>(a.preds + 2 * (size_t)map) = make_float2(x, y);
+    a.maxvals[map] = v;
+  }
+  if (a.argmax != nullptr) a.argmax[map] = idx;
+}
+
+// ------------------------------------------------------------------------------------------
+// mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------
+// Bulk-copy kernel.  Requires (H*W) % 4 == 0 and a 16-byte aligned `hm`.
+//   kWarps    warps per CTA (one CTA per SM)
+//   kStages   ring depth per warp
+//   kChunk    floats per stage (multiple of 128)
+struct Pending {  // a decoded map waiting for its epilogue
+  float v;
+  int idx;
+  float nb[4];  // left, right, up, down (single-stage maps only)
+};
+
+template <int kWarps, int kStages, int kChunk, int kBatch>
+struct BulkLayout {
+  static constexpr size_t ring_bytes = (size_t)kWarps * kStages * kChunk * sizeof(float);
+  static constexpr size_t pend_bytes = (size_t)kWarps * kBatch * sizeof(Pending);
+  static constexpr size_t bar_bytes = (size_t)kWarps * kStages * sizeof(uint64_t);
+  static constexpr size_t total = ring_bytes + pend_bytes + bar_bytes;
+};
+
+template <int kWarps, int kStages, int kChunk, int kBatch>
+__global__ void __launch_bounds__(kWarps * 32, 1) decode_bulk_kernel(const DecodeArgs a) {
+  static_assert(kBatch <= 32, "one pending map per lane");
+  using Layout = BulkLayout<kWarps, kStages, kChunk, kBatch>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* ring = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kStages * kChunk;
+  Pending* pend = reinterpret_cast<Pending*>(smem_raw + Layout::ring_bytes) + warp * kBatch;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + Layout::ring_bytes + Layout::pend_bytes) + warp * kStages;
+
+  const int hw = a.H * a.W;
+  const int chunks_per_map = (hw + kChunk - 1) / kChunk;
+  const bool single = chunks_per_map == 1;
+  const int n_warps = gridDim.x * kWarps;
+  const int gwarp = blockIdx.x * kWarps + warp;
+  // maps gwarp, gwarp + n_warps, ... -> a flat sequence of chunks for this warp
+  const int my_maps = (a.n_maps > gwarp) ? (a.n_maps - gwarp + n_warps - 1) / n_warps : 0;
+  const long long my_chunks = (long long)my_maps * chunks_per_map;
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  const uint64_t policy = evict_first_policy();
+  auto issue = [&](long long c) {  // lane 0 only
+    const int mi = (int)(c / chunks_per_map), ci = (int)(c - (long long)mi * chunks_per_map);
+    const int map = gwarp + mi * n_warps;
+    const int off = ci * kChunk;
+    const int n = min(kChunk, hw - off);
+    const int s = (int)(c % kStages);
+    const uint32_t bar = smem_u32(&bars[s]);
+    mbar_expect_tx(bar, (uint32_t)n * 4u);
+    bulk_g2s(smem_u32(ring + (size_t)s * kChunk), a.hm + (size_t)map * hw + off, (uint32_t)n * 4u, bar, policy);
+  };
+  if (lane == 0) {
+    for (long long c = 0; c < my_chunks && c < kStages; ++c) issue(c);
+  }
+
+  // epilogue of the maps parked in `pend`: entry e belongs to map (first_mi + e)
+  auto flush = [&](int first_mi, int count) {
+    __syncwarp();
+    if (lane < count) {
+      const Pending p = pend[lane];
+      const int map = gwarp + (first_mi + lane) * n_warps;
+      if (single) {
+        finish_map(a, map, p.v, p.idx, [&](float& l, float& r, float& u, float& d) {
+          l = p.nb[0], r = p.nb[1], u = p.nb[2], d = p.nb[3];
+        });
+      } else {
+        const float* g = a.hm + (size_t)map * hw + p.idx;
+        finish_map(a, map, p.v, p.idx, [&](float& l, float& r, float& u, float& d) {
+          l = __ldg(g - 1), r = __ldg(g + 1), u = __ldg(g - a.W), d = __ldg(g + a.W);
+        });
+      }
+    }
+    __syncwarp();
+  };
+
+  Best acc[4];
+  int n_pend = 0, pend_first = 0;
+  int mi = 0, ci = 0;
+  for (long long c = 0; c < my_chunks; ++c) {
+    const int map = gwarp + mi * n_warps;
+    const int off = ci * kChunk;
+    const int n = min(kChunk, hw - off);
+    const int s = (int)(c % kStages);
+    const float* stage = ring + (size_t)s * kChunk;
+    if (ci == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] = Best{-INFINITY, kNoIndex};
+    }
+    mbar_wait(smem_u32(&bars[s]), (uint32_t)((c / kStages) & 1));
+
+    const int nvec = n >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(stage);
+    int ebase = off + 4 * lane;
+#pragma unroll 4
+    for (int v = lane; v < nvec; v += 32, ebase += 128) {
+      const float4 q = v4[v];
+      take(acc[0], q.x, ebase);
+      take(acc[1], q.y, ebase);
+      take(acc[2], q.z, ebase);
+      take(acc[3], q.w, ebase);
+    }
+
+    if (ci == chunks_per_map - 1) {
+      // A lane that never saw a value above -inf still owns its first element (all -inf maps).
+      const bool owns = 4 * lane < hw;
+      Best b{acc[0].v, acc[0].i == kNoIndex ? 4 * lane : acc[0].i};
+#pragma unroll
+      for (int k = 1; k < 4; ++k) merge(b, acc[k].v, (acc[k].i == kNoIndex ? 4 * lane : acc[k].i) + k);
+      if (!owns) b = Best{-INFINITY, kNoIndex};
+      b = warp_merge(b);
+      if (b.v != b.v) b.i = first_nan_index(a.hm + (size_t)map * hw, hw, lane);
+      if (n_pend == 0) pend_first = mi;
+      if (lane == 0) {
+        pend[n_pend].v = b.v;
+        pend[n_pend].idx = b.i;
+      }
+      if (single && lane < 4) {
+        // clamped so the read stays inside the stage; finish_map ignores it when out of range
+        const int d = (lane == 0) ? -1 : (lane == 1) ? 1 : (lane == 2) ? -a.W : a.W;
+        pend[n_pend].nb[lane] = stage[min(max(b.i + d, 0), hw - 1)];
+      }
+      ++n_pend;
+    }
+    __syncwarp();  // every lane is done with this stage
+    if (lane == 0 && c + kStages < my_chunks) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async overwrite
+      issue(c + kStages);
+    }
+    if (n_pend == kBatch) {
+      flush(pend_first, kBatch);
+      n_pend = 0;
+    }
+    if (++ci == chunks_per_map) {
+      ci = 0;
+      ++mi;
+    }
+  }
+  if (n_pend > 0) flush(pend_first, n_pend);
+}
+
+// ------------------------------------------------------------------------------------------
+// Fallback for maps that are not 16-byte aligned: warp per map, coalesced scalar loads.
+constexpr int kPlainWarps = 4;
+
+__global__ void __launch_bounds__(kPlainWarps * 32) decode_plain_kernel(const DecodeArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hw = a.H * a.W;
+  const int n_warps = gridDim.x * kPlainWarps;
+  for (int map = blockIdx.x * kPlainWarps + warp; map < a.n_maps; map += n_warps) {
+    const float* g = a.hm + (size_t)map * hw;
+    Best b{-INFINITY, kNoIndex};
+#pragma unroll 4
+    for (int e = lane; e < hw; e += 32) take(b, __ldg(g + e), e);
+    if (b.i == kNoIndex && lane < hw) b.i = lane;
+    b = warp_merge(b);
+    if (b.v != b.v) b.i = first_nan_index(g, hw, lane);
+    if (lane == 0) {
+      const float* gi = g + b.i;
+      finish_map(a, map, b.v, b.i, [&](float& l, float& r, float& u, float& d) {
+        l = __ldg(gi - 1), r = __ldg(gi + 1), u = __ldg(gi - a.W), d = __ldg(gi + a.W);
+      });
+    }
+  }
+}
+
+int g_num_sms = 0;
+
+template <int kWarps, int kStages, int kChunk, int kBatch = 32>
+cudaError_t launch_bulk(const DecodeArgs& a, cudaStream_t stream) {
+  constexpr size_t smem = BulkLayout<kWarps, kStages, kChunk, kBatch>::total;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(decode_bulk_kernel<kWarps, kStages, kChunk, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int ctas_needed = (a.n_maps + kWarps - 1) / kWarps;
+  const int grid = ctas_needed < g_num_sms ? ctas_needed : g_num_sms;
+  decode_bulk_kernel<kWarps, kStages, kChunk, kBatch><<<grid, kWarps * 32, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+int g_decode_variant = 0;  // dev knob (SPE_DECODE_VARIANT): picks the warps x stages x chunk shape
+
+cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
+  if (a.n_maps == 0) return cudaSuccess;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    if (const char* v = getenv("SPE_DECODE_VARIANT")) g_decode_variant = atoi(v);
+  }
+  const long long hw = (long long)a.H * a.W;
+  const bool aligned = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.hm) & 15u) == 0);
+  if (aligned) {
+    switch (g_decode_variant) {
+      case 1: return launch_bulk<4, 3, 4096>(a, stream);   // 192 KB, 4 warps
+      case 2: return launch_bulk<8, 3, 2048>(a, stream);   // 192 KB, 8 warps, 8 KB stages
+      case 3: return launch_bulk<12, 2, 2048>(a, stream);  // 192 KB, 12 warps
+      case 4: return launch_bulk<6, 2, 4096>(a, stream);   // 192 KB, 6 warps
+      case 6: return launch_bulk<12, 1, 4096>(a, stream);  // 192 KB: 12 warps, one 16 KB stage each
+      case 7: return launch_bulk<13, 1, 4096, 16>(a, stream);
+      case 5: return launch_bulk<7, 2, 4096, 16>(a, stream);  // 224 KB: 7 warps x 2 stages x 16 KB
+      default: return launch_bulk<6, 2, 4096>(a, stream);  // 192 KB: 6 warps x 2 stages x 16 KB
+    }
+  }
+  const int ctas_needed = (a.n_maps + kPlainWarps - 1) / kPlainWarps;
+  const int cap = g_num_sms * 8;
+  decode_plain_kernel<<<ctas_needed < cap ? ctas_needed : cap, kPlainWarps * 32, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace spe

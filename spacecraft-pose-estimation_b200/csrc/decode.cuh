@@ -1,0 +1,22 @@
+// Internal interface between the C ABI (capi.cu) and the decode kernels (decode.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace spe {
+
+struct DecodeArgs {
+  const float* hm;      // [n_maps, H, W]
+  int n_maps, J, H, W;  // n_maps = B * J
+  const float* center;  // [B,2] or nullptr (get_max_preds: no affine, no refine)
+  const float* scale;   // [B,2]
+  int post_process;
+  float* preds;     // [n_maps,2]   (used when kpts == nullptr)
+  float* maxvals;   // [n_maps]
+  float* kpts;      // [n_maps,3]   (x, y, maxval) or nullptr
+  int32_t* argmax;  // [n_maps] or nullptr
+};
+
+cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream);
+
+}  // namespace spe

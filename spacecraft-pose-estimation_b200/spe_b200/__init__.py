@@ -1,0 +1,13 @@
+"""spe_b200 — B200-native heatmap -> 6-DoF pose stage of mohsij/spacecraft-pose-estimation.
+
+Public surface (mirrors the reference's call sites):
+    get_max_preds, get_final_preds        (landmark_regression/lib/core/inference.py)
+    PnPSolver.solve / solvePnPRansac      (pose_estimation/export_predicted_poses_real.py:177-204)
+    HeatmapToPose                         decode + pose without leaving the device, sharded over ranks
+The arithmetic lives in libspe_b200.so (CUDA, sm_100a) behind include/spe_b200.h.
+"""
+from . import models, synth  # noqa: F401
+from ._lib import LIB_PATH, SpeError  # noqa: F401
+from .inference import decode_device, get_final_preds, get_max_preds  # noqa: F401
+
+__all__ = ["get_max_preds", "get_final_preds", "decode_device", "models", "synth", "SpeError", "LIB_PATH"]
