@@ -114,9 +114,9 @@ int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int 
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Per-hypothesis scores of the most recent spe_ransac_epnp_f32 call on this workspace, for the
- * parity tests: counts [B,hypotheses] uint8-as-int32 and masks [B,hypotheses] uint32 (DEVICE). */
-int spe_ransac_debug_scores(const void* workspace, int B, int hypotheses, int32_t* counts,
-                            uint32_t* masks, void* stream);
+ * parity tests: counts [B,hypotheses] int32 and masks [B,hypotheses] uint32 (DEVICE). */
+int spe_ransac_debug_scores(const spe_model_t* model, const void* workspace, int B, int hypotheses,
+                            int32_t* counts, uint32_t* masks, void* stream);
 
 /* decode + pose with the keypoints kept in HBM; kpts_out [B,J,3] may be NULL only if workspace
  * has room (it always does: spe_pipeline_workspace_bytes accounts for it). */

@@ -1,8 +1,12 @@
 // C ABI of the heatmap -> pose stage (include/spe_b200.h).  Argument checking and launches only.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "../../include/spe_b200.h"
 #include "decode.cuh"
+#include "ransac.cuh"
+
+#include <new>
 
 namespace {
 
@@ -71,6 +75,122 @@ int spe_decode_kpts_f32(const float* hm, int B, int J, int H, int W, const float
                         float* kpts, int32_t* argmax, void* stream) {
   if (center == nullptr || scale == nullptr || kpts == nullptr) return B == 0 ? SPE_OK : SPE_ERR_INVALID_ARGUMENT;
   return run_decode(hm, B, J, H, W, center, scale, post_process, nullptr, nullptr, kpts, argmax, stream);
+}
+
+// ---- pose ----------------------------------------------------------------------------------
+struct spe_model {
+  spe::Model m;
+};
+
+int spe_pnp_model_create(const double* landmarks, int J, const double* K, const double* dist, int max_hypotheses, spe_model_t** out) {
+  if (out == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  if (landmarks == nullptr || K == nullptr || J < 4 || J > SPE_MAX_LANDMARKS) return SPE_ERR_INVALID_ARGUMENT;
+  if (max_hypotheses < 1 || max_hypotheses > SPE_MAX_HYPOTHESES) return SPE_ERR_INVALID_ARGUMENT;
+  spe_model* h = new (std::nothrow) spe_model();
+  if (h == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  spe::Model& m = h->m;
+  m.J = J;
+  m.max_hyp = max_hypotheses;
+  for (int i = 0; i < 3 * J; ++i) m.landmarks_f32[i] = (float)landmarks[i];
+  m.cam.fx = K[0], m.cam.cx = K[2], m.cam.fy = K[4], m.cam.cy = K[5];
+  m.cam.k1 = dist ? dist[0] : 0.0, m.cam.k2 = dist ? dist[1] : 0.0, m.cam.p1 = dist ? dist[2] : 0.0;
+  m.cam.p2 = dist ? dist[3] : 0.0, m.cam.k3 = dist ? dist[4] : 0.0;
+  const cudaError_t e = spe::model_upload(m);
+  if (e != cudaSuccess) {
+    spe::model_free(m);
+    delete h;
+    return cuda_fail(e);
+  }
+  *out = h;
+  return SPE_OK;
+}
+
+int spe_pnp_model_destroy(spe_model_t* model) {
+  if (model == nullptr) return SPE_OK;
+  spe::model_free(model->m);
+  delete model;
+  return SPE_OK;
+}
+
+int spe_pnp_model_num_landmarks(const spe_model_t* model) { return model ? model->m.J : SPE_ERR_INVALID_ARGUMENT; }
+
+int spe_pnp_model_minimal_sets(const spe_model_t* model, int n, int count, int32_t* out) {
+  if (model == nullptr || out == nullptr || n < 6 || n > model->m.J || count < 0 || count > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
+  const uint8_t* t = model->m.h_subsets.data() + (size_t)(n - 6) * model->m.max_hyp * spe::kModelPoints;
+  for (int i = 0; i < count * spe::kModelPoints; ++i) out[i] = t[i];
+  return SPE_OK;
+}
+
+size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypotheses) {
+  if (model == nullptr || B < 0 || hypotheses < 1) return 0;
+  return spe::ransac_workspace_bytes(model->m.J, B, hypotheses);
+}
+
+static int jacobi_sweeps_setting() {
+  static int sweeps = [] {
+    const char* v = getenv("SPE_JACOBI_SWEEPS");  // dev knob
+    const int s = v ? atoi(v) : 6;
+    return s > 0 && s <= 30 ? s : 6;
+  }();
+  return sweeps;
+}
+
+int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, double confidence,
+                        float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (model == nullptr || B < 0 || hypotheses < 1 || hypotheses > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SPE_OK;
+  if (kpts == nullptr || pose7 == nullptr || inlier_mask == nullptr || status == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  if (!(reproj_err > 0.f)) return SPE_ERR_INVALID_ARGUMENT;
+  const size_t need = spe::ransac_workspace_bytes(model->m.J, B, hypotheses);
+  if (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return SPE_ERR_WORKSPACE;
+  spe::RansacArgs a{};
+  a.kpts = kpts;
+  a.B = B;
+  a.H = hypotheses;
+  a.reproj_err = reproj_err;
+  a.confidence = confidence;
+  a.conf_floor = conf_floor;
+  a.jacobi_sweeps = jacobi_sweeps_setting();
+  a.pose7 = pose7;
+  a.inlier_mask = inlier_mask;
+  a.status = status;
+  a.winner = winner_hyp;
+  a.rt = rt;
+  const spe::RansacWorkspace ws = spe::carve_workspace(workspace, model->m.J, B, hypotheses);
+  const cudaError_t e = spe::launch_ransac_epnp(model->m, a, ws, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
+int spe_ransac_debug_scores(const spe_model_t* model, const void* workspace, int B, int hypotheses, int32_t* counts, uint32_t* masks,
+                            void* stream) {
+  if (model == nullptr || workspace == nullptr || B < 0 || hypotheses < 1) return SPE_ERR_INVALID_ARGUMENT;
+  const spe::RansacWorkspace ws = spe::carve_workspace(const_cast<void*>(workspace), model->m.J, B, hypotheses);
+  const cudaError_t e = spe::launch_debug_scores(ws, B, hypotheses, counts, masks, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
+size_t spe_pipeline_workspace_bytes(const spe_model_t* model, int B, int J, int hypotheses) {
+  if (model == nullptr || B < 0 || hypotheses < 1 || J != model->m.J) return 0;
+  const size_t kp = ((size_t)B * J * 3 * sizeof(float) + 15) & ~(size_t)15;
+  return kp + spe::ransac_workspace_bytes(J, B, hypotheses);
+}
+
+int spe_heatmap_to_pose_f32(const spe_model_t* model, const float* hm, int B, int J, int H, int W, const float* center,
+                            const float* scale, int post_process, int hypotheses, float reproj_err, double confidence,
+                            float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, float* kpts_out, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (model == nullptr || J != model->m.J) return SPE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SPE_OK;
+  const size_t need = spe_pipeline_workspace_bytes(model, B, J, hypotheses);
+  if (workspace == nullptr || need == 0 || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return SPE_ERR_WORKSPACE;
+  const size_t kp = ((size_t)B * J * 3 * sizeof(float) + 15) & ~(size_t)15;
+  float* kpts = kpts_out ? kpts_out : static_cast<float*>(workspace);
+  int rc = spe_decode_kpts_f32(hm, B, J, H, W, center, scale, post_process, kpts, nullptr, stream);
+  if (rc != SPE_OK) return rc;
+  return spe_ransac_epnp_f32(model, kpts, B, hypotheses, reproj_err, confidence, conf_floor, pose7, inlier_mask, status, nullptr, nullptr,
+                             static_cast<unsigned char*>(workspace) + kp, workspace_bytes - kp, stream);
 }
 
 }  // extern "C"

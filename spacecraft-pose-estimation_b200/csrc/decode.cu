@@ -375,11 +375,11 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
       case 1: return launch_bulk<4, 3, 4096>(a, stream);   // 192 KB, 4 warps
       case 2: return launch_bulk<8, 3, 2048>(a, stream);   // 192 KB, 8 warps, 8 KB stages
       case 3: return launch_bulk<12, 2, 2048>(a, stream);  // 192 KB, 12 warps
-      case 4: return launch_bulk<6, 2, 4096>(a, stream);   // 192 KB, 6 warps
-      case 6: return launch_bulk<12, 1, 4096>(a, stream);  // 192 KB: 12 warps, one 16 KB stage each
-      case 7: return launch_bulk<13, 1, 4096, 16>(a, stream);
+      case 4: return launch_bulk<6, 2, 4096>(a, stream);   // 192 KB, 6 warps x 2 stages x 16 KB
       case 5: return launch_bulk<7, 2, 4096, 16>(a, stream);  // 224 KB: 7 warps x 2 stages x 16 KB
-      default: return launch_bulk<6, 2, 4096>(a, stream);  // 192 KB: 6 warps x 2 stages x 16 KB
+      // measured best on B200 (profiles/decode_variants_r1.md): 12 warps, one 16 KB stage each,
+      // 192 KB of bulk copies in flight per SM, 64x64 maps refine from shared memory
+      default: return launch_bulk<12, 1, 4096>(a, stream);
     }
   }
   const int ctas_needed = (a.n_maps + kPlainWarps - 1) / kPlainWarps;

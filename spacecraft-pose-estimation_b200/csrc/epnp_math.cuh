@@ -1,0 +1,298 @@
+// Small dense linear algebra shared by the RANSAC-EPnP kernels (ransac_epnp.cu).
+//
+// Everything is templated on the scalar type: float for the per-hypothesis kernel (FP32 CUDA
+// cores, everything in registers, loops fully unrolled), double for the one final refit per frame.
+// The algorithm is OpenCV's EPnP (calib3d, un-vendored dependency of the reference; restated in
+// SURVEY.md App. B.3 and oracle/epnp_ref.py): control points -> M -> null-space basis -> three
+// linearised beta initialisations -> 5 Gauss-Newton steps each -> Procrustes -> best of three.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace spe {
+
+template <typename T>
+struct Real;
+template <>
+struct Real<float> {
+  static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+  static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float copysign(float m, float s) { return copysignf(m, s); }
+  static constexpr float eps = 1.1920929e-7f;
+  static constexpr float tiny = 1e-30f;
+  static constexpr int svd3_sweeps = 5;
+};
+template <>
+struct Real<double> {
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  static __device__ __forceinline__ double abs(double x) { return fabs(x); }
+  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ double copysign(double m, double s) { return ::copysign(m, s); }
+  static constexpr double eps = 2.220446049250313e-16;
+  static constexpr double tiny = 1e-280;
+  static constexpr int svd3_sweeps = 8;
+};
+
+// Jacobi rotation that orthogonalises two columns with squared norms (a, b) and inner product p:
+// returns (c, s, t = s/c) of  x' = c x - s y,  y' = s x + c y;  new norms a - t p, b + t p.
+template <typename T>
+__device__ __forceinline__ void jacobi_angle(T a, T b, T p, T& c, T& s, T& t) {
+  const T zeta = (b - a) / (T(2) * p);
+  t = Real<T>::copysign(T(1), zeta) / (Real<T>::abs(zeta) + Real<T>::sqrt(T(1) + zeta * zeta));
+  c = Real<T>::rsqrt(T(1) + t * t);
+  s = c * t;
+}
+
+// Householder least squares min |A x - b| for a tiny R x C system held in registers.
+// Zero (masked) columns are skipped and get x = 0.  A and b are overwritten.
+template <typename T, int R, int C>
+__device__ __forceinline__ void lsq_householder(T (&A)[R][C], T (&b)[R], T (&x)[C]) {
+  T diag[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    T s2 = T(0);
+#pragma unroll
+    for (int i = k; i < R; ++i) s2 += A[i][k] * A[i][k];
+    const T norm = Real<T>::sqrt(s2);
+    const T akk = A[k][k];
+    const T alpha = akk > T(0) ? -norm : norm;  // R_kk
+    const T vk = akk - alpha;
+    const T denom = -alpha * vk;  // = v^T v / 2  (>= norm^2)
+    const T inv = denom > Real<T>::tiny ? T(1) / denom : T(0);
+    A[k][k] = vk;
+#pragma unroll
+    for (int j = k + 1; j < C; ++j) {
+      T dot = T(0);
+#pragma unroll
+      for (int i = k; i < R; ++i) dot += A[i][k] * A[i][j];
+      const T tau = dot * inv;
+#pragma unroll
+      for (int i = k; i < R; ++i) A[i][j] -= tau * A[i][k];
+    }
+    T dot = T(0);
+#pragma unroll
+    for (int i = k; i < R; ++i) dot += A[i][k] * b[i];
+    const T tau = dot * inv;
+#pragma unroll
+    for (int i = k; i < R; ++i) b[i] -= tau * A[i][k];
+    diag[k] = alpha;
+  }
+#pragma unroll
+  for (int k = C - 1; k >= 0; --k) {
+    T acc = b[k];
+#pragma unroll
+    for (int j = k + 1; j < C; ++j) acc -= A[k][j] * x[j];
+    x[k] = Real<T>::abs(diag[k]) > Real<T>::tiny ? acc / diag[k] : T(0);
+  }
+}
+
+// L (6x10) from the four null-space candidates v[i][0..11] (four 3-vectors each); App. B.3g.
+template <typename T>
+__device__ __forceinline__ void build_L(const T (&v)[4][12], T (&L)[6][10]) {
+  constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    T d[4][3];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) d[i][c] = v[i][3 * pa[k] + c] - v[i][3 * pb[k] + c];
+    auto dot = [&](int i, int j) { return d[i][0] * d[j][0] + d[i][1] * d[j][1] + d[i][2] * d[j][2]; };
+    L[k][0] = dot(0, 0);
+    L[k][1] = T(2) * dot(0, 1);
+    L[k][2] = dot(1, 1);
+    L[k][3] = T(2) * dot(0, 2);
+    L[k][4] = T(2) * dot(1, 2);
+    L[k][5] = dot(2, 2);
+    L[k][6] = T(2) * dot(0, 3);
+    L[k][7] = T(2) * dot(1, 3);
+    L[k][8] = T(2) * dot(2, 3);
+    L[k][9] = dot(3, 3);
+  }
+}
+
+// rho_k = |c_a - c_b|^2 over the six control-point pairs.
+template <typename T>
+__device__ __forceinline__ void build_rho(const T (&cws)[4][3], T (&rho)[6]) {
+  constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const T dx = cws[pa[k]][0] - cws[pb[k]][0], dy = cws[pa[k]][1] - cws[pb[k]][1], dz = cws[pa[k]][2] - cws[pb[k]][2];
+    rho[k] = dx * dx + dy * dy + dz * dz;
+  }
+}
+
+// The three linearised initialisations of EPnP (App. B.3h), variant = 1, 2 or 3, as one piece
+// of straight-line code so that lanes running different variants do not diverge.
+template <typename T>
+__device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)[6], int variant, T (&betas)[4]) {
+  T A[6][5], b[6], x[5];
+  const bool v1 = variant == 1, v3 = variant == 3;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    A[k][0] = L[k][0];
+    A[k][1] = L[k][1];
+    A[k][2] = v1 ? L[k][3] : L[k][2];
+    A[k][3] = v1 ? L[k][6] : (v3 ? L[k][3] : T(0));
+    A[k][4] = v3 ? L[k][4] : T(0);
+    b[k] = rho[k];
+  }
+  lsq_householder<T, 6, 5>(A, b, x);
+  const bool neg = x[0] < T(0);
+  const T b0mag = Real<T>::sqrt(Real<T>::abs(x[0]));
+  if (v1) {
+    const T sg = neg ? T(-1) : T(1);
+    betas[0] = b0mag;
+    betas[1] = sg * x[1] / b0mag;
+    betas[2] = sg * x[2] / b0mag;
+    betas[3] = sg * x[3] / b0mag;
+  } else {
+    const bool same_sign = neg ? (x[2] < T(0)) : (x[2] > T(0));
+    T b0 = b0mag;
+    if (x[1] < T(0)) b0 = -b0;
+    betas[0] = b0;
+    betas[1] = same_sign ? Real<T>::sqrt(Real<T>::abs(x[2])) : T(0);
+    betas[2] = v3 ? x[3] / b0 : T(0);
+    betas[3] = T(0);
+  }
+}
+
+// Exactly five Gauss-Newton steps on the six distance constraints (App. B.3i).
+template <typename T>
+__device__ __forceinline__ void gauss_newton(const T (&L)[6][10], const T (&rho)[6], T (&be)[4]) {
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    T A[6][4], r[6], x[4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const T* l = L[k];
+      A[k][0] = T(2) * l[0] * be[0] + l[1] * be[1] + l[3] * be[2] + l[6] * be[3];
+      A[k][1] = l[1] * be[0] + T(2) * l[2] * be[1] + l[4] * be[2] + l[7] * be[3];
+      A[k][2] = l[3] * be[0] + l[4] * be[1] + T(2) * l[5] * be[2] + l[8] * be[3];
+      A[k][3] = l[6] * be[0] + l[7] * be[1] + l[8] * be[2] + T(2) * l[9] * be[3];
+      r[k] = rho[k] - (l[0] * be[0] * be[0] + l[1] * be[0] * be[1] + l[2] * be[1] * be[1] + l[3] * be[0] * be[2] +
+                       l[4] * be[1] * be[2] + l[5] * be[2] * be[2] + l[6] * be[0] * be[3] + l[7] * be[1] * be[3] +
+                       l[8] * be[2] * be[3] + l[9] * be[3] * be[3]);
+    }
+    lsq_householder<T, 6, 4>(A, r, x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) be[i] += x[i];
+  }
+}
+
+// R = U V^T of the 3x3 matrix A = U S V^T (orthogonal Procrustes factor), by one-sided Jacobi.
+// The left vector of the smallest singular value is rebuilt as a cross product so that nearly
+// planar configurations stay orthonormal; its sign follows the rotated column, which preserves
+// det(U V^T) exactly as a full SVD would give it.
+template <typename T>
+__device__ __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3]) {
+  T B[3][3], V[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      B[i][j] = A[i][j];
+      V[i][j] = i == j ? T(1) : T(0);
+    }
+#pragma unroll 1
+  for (int sweep = 0; sweep < Real<T>::svd3_sweeps; ++sweep) {
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      const T a = B[0][p] * B[0][p] + B[1][p] * B[1][p] + B[2][p] * B[2][p];
+      const T b = B[0][q] * B[0][q] + B[1][q] * B[1][q] + B[2][q] * B[2][q];
+      const T g = B[0][p] * B[0][q] + B[1][p] * B[1][q] + B[2][p] * B[2][q];
+      const bool rot = g * g > (Real<T>::eps * Real<T>::eps) * a * b;
+      T c, s, t;
+      jacobi_angle<T>(a, b, rot ? g : T(1), c, s, t);
+      c = rot ? c : T(1);
+      s = rot ? s : T(0);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const T x = B[r][p], y = B[r][q];
+        B[r][p] = c * x - s * y;
+        B[r][q] = s * x + c * y;
+        const T vx = V[r][p], vy = V[r][q];
+        V[r][p] = c * vx - s * vy;
+        V[r][q] = s * vx + c * vy;
+      }
+    }
+  }
+  T n2[3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) n2[j] = B[0][j] * B[0][j] + B[1][j] * B[1][j] + B[2][j] * B[2][j];
+  const int jmin = (n2[0] <= n2[1] && n2[0] <= n2[2]) ? 0 : (n2[1] <= n2[2] ? 1 : 2);
+  T U[3][3];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    const T inv = Real<T>::rsqrt(n2[j] > Real<T>::tiny ? n2[j] : T(1));
+#pragma unroll
+    for (int r = 0; r < 3; ++r) U[r][j] = B[r][j] * inv;
+  }
+  // rebuild column jmin from the other two (cyclic order keeps the orientation bookkeeping simple)
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (j == jmin) {
+      const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+      T cx = U[1][j1] * U[2][j2] - U[2][j1] * U[1][j2];
+      T cy = U[2][j1] * U[0][j2] - U[0][j1] * U[2][j2];
+      T cz = U[0][j1] * U[1][j2] - U[1][j1] * U[0][j2];
+      const T along = cx * B[0][j] + cy * B[1][j] + cz * B[2][j];
+      const T sg = along < T(0) ? T(-1) : T(1);
+      U[0][j] = sg * cx;
+      U[1][j] = sg * cy;
+      U[2][j] = sg * cz;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) R[r][c] = U[r][0] * V[c][0] + U[r][1] * V[c][1] + U[r][2] * V[c][2];
+  // OpenCV's handling of a reflection: negate the third ROW of R (App. B.3j)
+  const T det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+  if (det < T(0)) {
+    R[2][0] = -R[2][0];
+    R[2][1] = -R[2][1];
+    R[2][2] = -R[2][2];
+  }
+}
+
+// cv_rotation_matrix_to_quat (pose_estimation/export_predicted_poses_real.py:22-57):
+// scalar-first quaternion, branch on the largest of the four candidate magnitudes.
+__device__ __forceinline__ void rotation_to_quat(const double (&r)[3][3], double (&q)[4]) {
+  const double e0 = sqrt(fmax(1.0 + r[0][0] + r[1][1] + r[2][2], 0.0)) * 0.5;
+  const double e1 = sqrt(fmax(1.0 + r[0][0] - r[1][1] - r[2][2], 0.0)) * 0.5;
+  const double e2 = sqrt(fmax(1.0 - r[0][0] + r[1][1] - r[2][2], 0.0)) * 0.5;
+  const double e3 = sqrt(fmax(1.0 - r[0][0] - r[1][1] + r[2][2], 0.0)) * 0.5;
+  int m = 0;  // np.argmax: first maximum
+  double best = e0;
+  if (e1 > best) best = e1, m = 1;
+  if (e2 > best) best = e2, m = 2;
+  if (e3 > best) best = e3, m = 3;
+  if (m == 0) {
+    q[0] = e0;
+    q[1] = (r[2][1] - r[1][2]) / (4 * e0);
+    q[2] = (r[0][2] - r[2][0]) / (4 * e0);
+    q[3] = (r[1][0] - r[0][1]) / (4 * e0);
+  } else if (m == 1) {
+    q[0] = (r[2][1] - r[1][2]) / (4 * e1);
+    q[1] = e1;
+    q[2] = (r[1][0] + r[0][1]) / (4 * e1);
+    q[3] = (r[2][0] + r[0][2]) / (4 * e1);
+  } else if (m == 2) {
+    q[0] = (r[0][2] - r[2][0]) / (4 * e2);
+    q[1] = (r[1][0] + r[0][1]) / (4 * e2);
+    q[2] = e2;
+    q[3] = (r[2][1] + r[1][2]) / (4 * e2);
+  } else {
+    q[0] = (r[1][0] - r[0][1]) / (4 * e3);
+    q[1] = (r[2][0] + r[0][2]) / (4 * e3);
+    q[2] = (r[2][1] + r[1][2]) / (4 * e3);
+    q[3] = e3;
+  }
+}
+
+}  // namespace spe

@@ -1,0 +1,66 @@
+// Internal interface between the C ABI (capi.cu) and the RANSAC-EPnP kernels (ransac_epnp.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+namespace spe {
+
+constexpr int kMaxLandmarks = 32;
+constexpr int kModelPoints = 5;  // EPnP minimal set used by cv2.solvePnPRansac
+
+struct Camera {
+  double fx, fy, cx, cy;
+  double k1, k2, p1, p2, k3;
+};
+
+// Host-side model: immutable after creation.
+struct Model {
+  int J = 0;
+  int max_hyp = 0;
+  int device = 0;
+  Camera cam{};
+  float landmarks_f32[kMaxLandmarks * 3] = {};  // cv2 rounds object points to float32 on entry
+  float* d_landmarks = nullptr;                 // [J,3] float32
+  uint8_t* d_subsets = nullptr;                 // [J-5][max_hyp][5]: minimal sets for n = 6..J
+  std::vector<uint8_t> h_subsets;               // host copy of the same table
+};
+
+// Workspace carve-up for B frames x H hypotheses (all offsets 16-byte aligned).
+struct RansacWorkspace {
+  double2* und;      // [B,J] undistorted normalised coordinates (float64, for the final refit)
+  float2* us_hyp;    // [B,J] ideal pixel coordinates as float32 (for the hypotheses)
+  int32_t* n;        // [B] number of landmarks that passed the confidence filter
+  uint32_t* vis;     // [B] bit j = landmark j takes part
+  uint32_t* masks;   // [B,H] inlier mask of every hypothesis over the J landmarks
+  uint8_t* counts;   // [B,H] popcount of the above
+  size_t bytes;
+};
+
+size_t ransac_workspace_bytes(int J, int B, int H);
+RansacWorkspace carve_workspace(void* base, int J, int B, int H);
+
+struct RansacArgs {
+  const float* kpts;  // [B,J,3] (x, y, conf)
+  int B, H;
+  float reproj_err;
+  double confidence;
+  float conf_floor;  // < 0: the reference's adaptive filter
+  int jacobi_sweeps;
+  float* pose7;           // [B,7]
+  uint32_t* inlier_mask;  // [B]
+  int32_t* status;        // [B]
+  int32_t* winner;        // [B] or nullptr
+  double* rt;             // [B,12] or nullptr
+};
+
+cudaError_t model_upload(Model& m);
+void model_free(Model& m);
+cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_debug_scores(const RansacWorkspace& ws, int B, int H, int32_t* counts, uint32_t* masks, cudaStream_t stream);
+
+// OpenCV's RANSAC RNG: minimal sets for `count` points, draw order preserved.
+void opencv_minimal_sets(int count, int num, uint8_t* out /* [num][5] */);
+
+}  // namespace spe

@@ -1,0 +1,810 @@
+// Batched RANSAC-EPnP for sm_100a.
+//
+// Replaces the per-frame loop of pose_estimation/export_predicted_poses_real.py:177-204
+// (confidence filter, cv2.solvePnPRansac(flags=SOLVEPNP_EPNP, iterationsCount, reprojectionError),
+// cv2.Rodrigues, cv_rotation_matrix_to_quat).  OpenCV calib3d is an un-vendored dependency of the
+// reference; its algorithm is restated in SURVEY.md App. B and oracle/{ocv_rng,epnp_ref,pnp_ref}.py.
+//
+// Three kernels per call, all on one stream, no host synchronisation:
+//   1. frame_prep_kernel   warp per frame: confidence filter -> visible set, 5-iteration
+//                          undistortion of every landmark (float64, cv2.undistortPoints)
+//   2. hypothesis_kernel   FP32.  Every minimal set of OpenCV's fixed-seed RNG is scored; there is
+//                          no early exit on the GPU.  A group of 4 lanes owns one (frame, hypothesis):
+//                          the 10x12 matrix M and the 12x12 accumulator V are distributed by rows
+//                          over the 4 lanes (72 registers each) and orthogonalised by one-sided
+//                          Jacobi rotations — the Jacobi eigensolve of MtM applied implicitly, without
+//                          squaring M's condition number in FP32; dot products cross lanes with
+//                          two shuffles.  The three EPnP beta initialisations + Gauss-Newton +
+//                          Procrustes then run one variant per lane, and the inlier scoring is
+//                          split over the lanes again (shuffle OR of the inlier bits).
+//   3. select_refit_kernel replays cv2's sequential acceptance rule (first strictly better count,
+//                          adaptively shrinking iteration budget) over the H inlier counts, then
+//                          runs the final EPnP on the winner's inliers in float64, following
+//                          OpenCV operation by operation where signs depend on it (PCA axes).
+//
+// Compute-bound on FP32 CUDA cores (no tensor cores: nothing here is a dense contraction);
+// HBM traffic is ~100 B per hypothesis.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/spe_b200.h"
+#include "epnp_math.cuh"
+#include "ransac.cuh"
+
+namespace spe {
+
+// ------------------------------------------------------------------------------------------
+// OpenCV RNG (multiply-with-carry, seeded with (uint64)-1 on every RANSAC run)
+void opencv_minimal_sets(int count, int num, uint8_t* out) {
+  uint64_t state = ~0ull;
+  auto next = [&]() -> uint32_t {
+    state = (uint64_t)(uint32_t)state * 4164903690ull + (state >> 32);
+    return (uint32_t)state;
+  };
+  for (int h = 0; h < num; ++h) {
+    uint8_t* s = out + (size_t)h * kModelPoints;
+    for (int i = 0; i < kModelPoints; ++i) {
+      for (;;) {
+        const uint32_t v = next() % (uint32_t)count;
+        bool dup = false;
+        for (int k = 0; k < i; ++k) dup |= (s[k] == v);
+        if (!dup) {
+          s[i] = (uint8_t)v;
+          break;
+        }
+      }
+    }
+  }
+}
+
+cudaError_t model_upload(Model& m) {
+  cudaError_t e = cudaGetDevice(&m.device);
+  if (e != cudaSuccess) return e;
+  e = cudaMalloc(&m.d_landmarks, sizeof(float) * 3 * m.J);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpy(m.d_landmarks, m.landmarks_f32, sizeof(float) * 3 * m.J, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  const int tables = m.J >= 6 ? m.J - 5 : 0;
+  m.h_subsets.assign((size_t)tables * m.max_hyp * kModelPoints, 0);
+  for (int n = 6; n <= m.J; ++n) opencv_minimal_sets(n, m.max_hyp, m.h_subsets.data() + (size_t)(n - 6) * m.max_hyp * kModelPoints);
+  if (tables > 0) {
+    e = cudaMalloc(&m.d_subsets, m.h_subsets.size());
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(m.d_subsets, m.h_subsets.data(), m.h_subsets.size(), cudaMemcpyHostToDevice);
+  }
+  return e;
+}
+
+void model_free(Model& m) {
+  if (m.d_landmarks) cudaFree(m.d_landmarks);
+  if (m.d_subsets) cudaFree(m.d_subsets);
+  m.d_landmarks = nullptr;
+  m.d_subsets = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+static size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+RansacWorkspace carve_workspace(void* base, int J, int B, int H) {
+  RansacWorkspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<unsigned char*>(base) + off : nullptr;
+    off += align16(bytes);
+    return p;
+  };
+  w.und = static_cast<double2*>(take(sizeof(double2) * (size_t)B * J));
+  w.us_hyp = static_cast<float2*>(take(sizeof(float2) * (size_t)B * J));
+  w.n = static_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
+  w.vis = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B));
+  w.masks = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B * H));
+  w.counts = static_cast<uint8_t*>(take((size_t)B * H));
+  w.bytes = off;
+  return w;
+}
+
+size_t ransac_workspace_bytes(int J, int B, int H) { return carve_workspace(nullptr, J, B, H).bytes; }
+
+namespace {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+struct DevModel {
+  const float* landmarks;  // [J,3]
+  const uint8_t* subsets;  // [J-5][max_hyp][5]
+  int J, max_hyp;
+  Camera cam;
+};
+
+// ------------------------------------------------------------------------------------------
+// 1. per-frame preparation: warp per frame, lane j = landmark j
+__global__ void __launch_bounds__(128) frame_prep_kernel(DevModel m, const float* __restrict__ kpts, int B, float conf_floor,
+                                                          RansacWorkspace ws) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const bool has = lane < m.J;
+  float u = 0.f, v = 0.f, conf = -1.f;
+  if (has) {
+    const float* k = kpts + ((size_t)b * m.J + lane) * 3;
+    u = k[0], v = k[1], conf = k[2];
+  }
+  unsigned vis;
+  if (conf_floor >= 0.f) {
+    vis = __ballot_sync(kFull, has && conf > conf_floor);
+  } else {
+    // export_predicted_poses_real.py:186-197: thr = 0.95, *= 0.8 while fewer than 15 pass (<= 100 times).
+    // thr lives in float64 (a Python float); the comparison happens in float32 (NumPy array dtype).
+    double thr = 0.95;
+    vis = __ballot_sync(kFull, has && conf > (float)thr);
+    for (int it = 0; it < 100 && __popc(vis) < 15; ++it) {
+      thr *= 0.8;
+      vis = __ballot_sync(kFull, has && conf > (float)thr);
+    }
+  }
+  if (has) {
+    // cv2.undistortPoints: exactly 5 fixed-point iterations in float64 (App. B.3a)
+    const Camera& c = m.cam;
+    const double x0 = ((double)u - c.cx) / c.fx, y0 = ((double)v - c.cy) / c.fy;
+    double x = x0, y = y0;
+#pragma unroll 1
+    for (int it = 0; it < 5; ++it) {
+      const double r2 = x * x + y * y;
+      const double icd = 1.0 / (1.0 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);
+      const double dx = 2.0 * c.p1 * x * y + c.p2 * (r2 + 2.0 * x * x);
+      const double dy = c.p1 * (r2 + 2.0 * y * y) + 2.0 * c.p2 * x * y;
+      x = (x0 - dx) * icd;
+      y = (y0 - dy) * icd;
+    }
+    ws.und[(size_t)b * m.J + lane] = make_double2(x, y);
+    // hypotheses see the float32-rounded normalised point (cv2 keeps the input dtype), mapped to
+    // ideal pixels in float64 by EPnP's init_points, then held in float32 by this implementation
+    const double xf = (double)(float)x, yf = (double)(float)y;
+    ws.us_hyp[(size_t)b * m.J + lane] = make_float2((float)(xf * c.fx + c.cx), (float)(yf * c.fy + c.cy));
+  }
+  if (lane == 0) {
+    ws.vis[b] = vis;
+    ws.n[b] = __popc(vis);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2. hypothesis kernel
+constexpr int kGroup = 4;                   // lanes per hypothesis
+constexpr int kHypPerCta = 32;              // 128 threads
+constexpr int kVStride = 4 * 12 + 20 + 1;   // v[4][12] + alphas[5][4] + pad (odd: conflict-free across groups)
+
+// round-robin (circle) schedule of the 66 column pairs of a sweep: 11 rounds x 6 disjoint pairs
+__host__ __device__ constexpr int rr_p(int r, int k) { return k == 0 ? r : (r + k) % 11; }
+__host__ __device__ constexpr int rr_q(int r, int k) { return k == 0 ? 11 : (r - k + 11) % 11; }
+
+__device__ __forceinline__ float group_sum(float x) {
+  x += __shfl_xor_sync(kFull, x, 1);
+  x += __shfl_xor_sync(kFull, x, 2);
+  return x;
+}
+
+// One-sided Jacobi on the columns of W = [M (rows spread over the 4 lanes); V].  Mr/Vr hold this
+// lane's 3 rows of each.  Equivalent to the Jacobi eigensolve of MtM with V accumulating the
+// eigenvectors; after convergence the column norms are the singular values of M.
+__device__ __forceinline__ void jacobi_sweeps(float (&Mr)[3][12], float (&Vr)[3][12], float (&d)[12], int sweeps) {
+  constexpr float kTol2 = 9e-14f;  // (3e-7)^2: skip pairs that are orthogonal to FP32 accuracy
+#pragma unroll 1
+  for (int sw = 0; sw < sweeps; ++sw) {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) d[j] = group_sum(Mr[0][j] * Mr[0][j] + Mr[1][j] * Mr[1][j] + Mr[2][j] * Mr[2][j]);
+#pragma unroll
+    for (int r = 0; r < 11; ++r) {
+      float g[6], c[6], s[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int p = rr_p(r, k), q = rr_q(r, k);
+        g[k] = Mr[0][p] * Mr[0][q] + Mr[1][p] * Mr[1][q] + Mr[2][p] * Mr[2][q];
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) g[k] += __shfl_xor_sync(kFull, g[k], 1);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) g[k] += __shfl_xor_sync(kFull, g[k], 2);
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int p = rr_p(r, k), q = rr_q(r, k);
+        const bool rot = g[k] * g[k] > kTol2 * d[p] * d[q];
+        float t;
+        jacobi_angle<float>(d[p], d[q], rot ? g[k] : 1.0f, c[k], s[k], t);
+        c[k] = rot ? c[k] : 1.0f;
+        s[k] = rot ? s[k] : 0.0f;
+        t = rot ? t : 0.0f;
+        d[p] = fmaxf(d[p] - t * g[k], 0.0f);
+        d[q] = fmaxf(d[q] + t * g[k], 0.0f);
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int p = rr_p(r, k), q = rr_q(r, k);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          const float x = Mr[i][p], y = Mr[i][q];
+          Mr[i][p] = c[k] * x - s[k] * y;
+          Mr[i][q] = s[k] * x + c[k] * y;
+          const float vx = Vr[i][p], vy = Vr[i][q];
+          Vr[i][p] = c[k] * vx - s[k] * vy;
+          Vr[i][q] = s[k] * vx + c[k] * vy;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) d[j] = group_sum(Mr[0][j] * Mr[0][j] + Mr[1][j] * Mr[1][j] + Mr[2][j] * Mr[2][j]);
+}
+
+// Control points and barycentric coordinates of a 5-point set (App. B.3c-d) without forming the
+// covariance: one-sided Jacobi on the centred 5x3 point matrix gives the PCA axes (columns of V)
+// and P0 V, whose column norms are sqrt(lambda).  Axis order/sign is free for a hypothesis.
+__device__ __forceinline__ void control_points5(const float (&pw)[5][3], float (&cws)[4][3], float (&al)[5][4]) {
+  float c0[3], Bm[5][3], V[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) c0[c] = (pw[0][c] + pw[1][c] + pw[2][c] + pw[3][c] + pw[4][c]) * 0.2f;
+#pragma unroll
+  for (int k = 0; k < 5; ++k)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) Bm[k][c] = pw[k][c] - c0[c];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.f : 0.f;
+#pragma unroll 1
+  for (int sweep = 0; sweep < 5; ++sweep) {
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      float a = 0.f, b = 0.f, g = 0.f;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        a += Bm[k][p] * Bm[k][p];
+        b += Bm[k][q] * Bm[k][q];
+        g += Bm[k][p] * Bm[k][q];
+      }
+      const bool rot = g * g > 1.4e-14f * a * b;
+      float c, s, t;
+      jacobi_angle<float>(a, b, rot ? g : 1.f, c, s, t);
+      c = rot ? c : 1.f;
+      s = rot ? s : 0.f;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float x = Bm[k][p], y = Bm[k][q];
+        Bm[k][p] = c * x - s * y;
+        Bm[k][q] = s * x + c * y;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float x = V[k][p], y = V[k][q];
+        V[k][p] = c * x - s * y;
+        V[k][q] = s * x + c * y;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) cws[0][c] = c0[c];
+  float inv_k[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    float s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) s2 += Bm[k][i] * Bm[k][i];
+    const float ki = sqrtf(s2 * 0.2f);  // sqrt(lambda_i / 5)
+    inv_k[i] = ki > 1e-12f ? 1.0f / ki : 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) cws[i + 1][c] = c0[c] + ki * V[c][i];
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    al[k][1] = Bm[k][0] * inv_k[0];
+    al[k][2] = Bm[k][1] * inv_k[1];
+    al[k][3] = Bm[k][2] * inv_k[2];
+    al[k][0] = 1.0f - al[k][1] - al[k][2] - al[k][3];
+  }
+}
+
+__global__ void __launch_bounds__(kHypPerCta * kGroup, 3)
+hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks, float thr2, int sweeps, RansacWorkspace ws) {
+  __shared__ float s_pw[kMaxLandmarks][3];
+  __shared__ float2 s_us[kMaxLandmarks];
+  __shared__ float2 s_img[kMaxLandmarks];
+  __shared__ float s_work[kHypPerCta][kVStride];
+
+  const int b = blockIdx.x / hblocks, hb = blockIdx.x - b * hblocks;
+  const int n = ws.n[b];
+  if (n <= kModelPoints) return;  // n < 6: no RANSAC (handled by the refit kernel); uniform per CTA
+  const unsigned vis = ws.vis[b];
+  const int tid = threadIdx.x;
+  if (tid < n) {  // compact the visible landmarks: position k <- k-th set bit of vis
+    const int j = __fns(vis, 0, tid + 1);
+    s_pw[tid][0] = m.landmarks[3 * j], s_pw[tid][1] = m.landmarks[3 * j + 1], s_pw[tid][2] = m.landmarks[3 * j + 2];
+    s_us[tid] = ws.us_hyp[(size_t)b * m.J + j];
+    const float* k = kpts + ((size_t)b * m.J + j) * 3;
+    s_img[tid] = make_float2(k[0], k[1]);
+  }
+  __syncthreads();
+
+  const int grp = tid >> 2, l = tid & 3;
+  const int h = hb * kHypPerCta + grp;
+  const bool live = h < H;
+  const uint8_t* sub = m.subsets + ((size_t)(n - 6) * m.max_hyp + (live ? h : 0)) * kModelPoints;
+  float* work = s_work[grp];
+  const float fu = (float)m.cam.fx, fv = (float)m.cam.fy, uc = (float)m.cam.cx, vc = (float)m.cam.cy;
+
+  // ---- control points, alphas, this lane's rows of M ---------------------------------------
+  float rho[6];
+  float Mr[3][12], Vr[3][12], d[12];
+  {
+    float pw[5][3], al[5][4], us[5][2], cws[4][3];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int si = sub[k];
+      pw[k][0] = s_pw[si][0], pw[k][1] = s_pw[si][1], pw[k][2] = s_pw[si][2];
+      us[k][0] = s_us[si].x, us[k][1] = s_us[si].y;
+    }
+    control_points5(pw, cws, al);
+    build_rho<float>(cws, rho);
+    if (l == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) work[48 + 4 * k + j] = al[k][j];
+    }
+    // rows l, l+4, l+8 of M: row r belongs to point r>>1, odd rows are the v-equations (App. B.3e)
+    const bool isv = l & 1, hi = l >> 1;
+#pragma unroll
+    for (int s = 0; s < 3; ++s) {
+      const bool valid = (s < 2) || (l < 2);
+      const int p0 = 2 * s, p1 = (2 * s + 1 < 5) ? 2 * s + 1 : 4;
+      const float uu = hi ? us[p1][0] : us[p0][0], vv = hi ? us[p1][1] : us[p0][1];
+      const float w = isv ? (vc - vv) : (uc - uu);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = hi ? al[p1][j] : al[p0][j];
+        a = valid ? a : 0.f;
+        Mr[s][3 * j] = isv ? 0.f : a * fu;
+        Mr[s][3 * j + 1] = isv ? a * fv : 0.f;
+        Mr[s][3 * j + 2] = a * w;
+      }
+#pragma unroll
+      for (int j = 0; j < 12; ++j) Vr[s][j] = (3 * l + s == j) ? 1.f : 0.f;
+    }
+  }
+
+  // ---- implicit Jacobi eigensolve of MtM -----------------------------------------------------
+  jacobi_sweeps(Mr, Vr, d, sweeps);
+
+  // the four smallest singular directions, ascending: v0 = smallest (OpenCV's ut[11]) ... v3
+  {
+    float dd[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) dd[j] = d[j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float best = dd[0];
+      int jb = 0;
+#pragma unroll
+      for (int j = 1; j < 12; ++j) {
+        const bool lt = dd[j] < best;
+        best = lt ? dd[j] : best;
+        jb = lt ? j : jb;
+      }
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) {
+        const bool sel = j == jb;
+        v0 = sel ? Vr[0][j] : v0;
+        v1 = sel ? Vr[1][j] : v1;
+        v2 = sel ? Vr[2][j] : v2;
+        dd[j] = sel ? INFINITY : dd[j];
+      }
+      work[12 * i + 3 * l + 0] = v0;
+      work[12 * i + 3 * l + 1] = v1;
+      work[12 * i + 3 * l + 2] = v2;
+    }
+  }
+  __syncwarp();
+
+  // ---- betas: one EPnP variant per lane (lane 3 repeats variant 1) ----------------------------
+  const int variant = l < 3 ? l + 1 : 1;
+  float betas[4];
+  {
+    float v[4][12], L[6][10];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 12; ++j) v[i][j] = work[12 * i + j];
+    build_L<float>(v, L);
+    approx_betas<float>(L, rho, variant, betas);
+    gauss_newton<float>(L, rho, betas);
+  }
+
+  // ---- camera-frame control points -> Procrustes -> reprojection error on the 5 points --------
+  float R[3][3], t[3], err;
+  {
+    float ccs[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        ccs[j][c] = betas[0] * work[3 * j + c] + betas[1] * work[12 + 3 * j + c] + betas[2] * work[24 + 3 * j + c] +
+                    betas[3] * work[36 + 3 * j + c];
+    float pcs[5][3], pw[5][3];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int si = sub[k];
+      pw[k][0] = s_pw[si][0], pw[k][1] = s_pw[si][1], pw[k][2] = s_pw[si][2];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        pcs[k][c] = work[48 + 4 * k] * ccs[0][c] + work[48 + 4 * k + 1] * ccs[1][c] + work[48 + 4 * k + 2] * ccs[2][c] +
+                    work[48 + 4 * k + 3] * ccs[3][c];
+    }
+    const float sgn = pcs[0][2] < 0.f ? -1.f : 1.f;  // solve_for_sign
+    float pc0[3] = {0.f, 0.f, 0.f}, pw0[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        pcs[k][c] *= sgn;
+        pc0[c] += pcs[k][c];
+        pw0[c] += pw[k][c];
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pc0[c] *= 0.2f, pw0[c] *= 0.2f;
+    float abt[3][3] = {};
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) abt[r][c] += (pcs[k][r] - pc0[r]) * (pw[k][c] - pw0[c]);
+    procrustes_uvt<float>(abt, R);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) t[r] = pc0[r] - (R[r][0] * pw0[0] + R[r][1] * pw0[1] + R[r][2] * pw0[2]);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const int si = sub[k];
+      const float Xc = R[0][0] * pw[k][0] + R[0][1] * pw[k][1] + R[0][2] * pw[k][2] + t[0];
+      const float Yc = R[1][0] * pw[k][0] + R[1][1] * pw[k][1] + R[1][2] * pw[k][2] + t[1];
+      const float iz = 1.0f / (R[2][0] * pw[k][0] + R[2][1] * pw[k][1] + R[2][2] * pw[k][2] + t[2]);
+      const float du = s_us[si].x - (uc + fu * Xc * iz), dv = s_us[si].y - (vc + fv * Yc * iz);
+      sum += sqrtf(du * du + dv * dv);
+    }
+    err = sum * 0.2f;
+  }
+
+  // ---- best of the three variants (App. B.3k), broadcast to the group -------------------------
+  {
+    const int base = (threadIdx.x & 31) & ~3;
+    const float e1 = __shfl_sync(kFull, err, base), e2 = __shfl_sync(kFull, err, base + 1), e3 = __shfl_sync(kFull, err, base + 2);
+    int N = 0;
+    if (e2 < e1) N = 1;
+    if (e3 < (N == 1 ? e2 : e1)) N = 2;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) R[r][c] = __shfl_sync(kFull, R[r][c], base + N);
+      t[r] = __shfl_sync(kFull, t[r], base + N);
+    }
+  }
+
+  // ---- score all n points: cv2.projectPoints + squared error <= reproj^2 (App. B.5) -----------
+  unsigned bits = 0;
+  {
+    const float k1 = (float)m.cam.k1, k2 = (float)m.cam.k2, p1 = (float)m.cam.p1, p2 = (float)m.cam.p2, k3 = (float)m.cam.k3;
+    for (int k = l; k < n; k += kGroup) {
+      const float X = s_pw[k][0], Y = s_pw[k][1], Z = s_pw[k][2];
+      const float xc = R[0][0] * X + R[0][1] * Y + R[0][2] * Z + t[0];
+      const float yc = R[1][0] * X + R[1][1] * Y + R[1][2] * Z + t[1];
+      const float zc = R[2][0] * X + R[2][1] * Y + R[2][2] * Z + t[2];
+      const float iz = 1.0f / zc;
+      const float x = xc * iz, y = yc * iz;
+      const float r2 = x * x + y * y;
+      const float cd = 1.0f + ((k3 * r2 + k2) * r2 + k1) * r2;
+      const float xd = x * cd + 2.0f * p1 * x * y + p2 * (r2 + 2.0f * x * x);
+      const float yd = y * cd + p1 * (r2 + 2.0f * y * y) + 2.0f * p2 * x * y;
+      const float du = s_img[k].x - (fu * xd + uc), dv = s_img[k].y - (fv * yd + vc);
+      const float e = du * du + dv * dv;
+      if (e <= thr2) bits |= 1u << __fns(vis, 0, k + 1);  // back to landmark numbering
+    }
+    bits |= __shfl_xor_sync(kFull, bits, 1);
+    bits |= __shfl_xor_sync(kFull, bits, 2);
+  }
+  if (live && l == 0) {
+    ws.masks[(size_t)b * H + h] = bits;
+    ws.counts[(size_t)b * H + h] = (uint8_t)__popc(bits);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3. selection + final refit (float64, one thread per frame)
+
+// OpenCV's JacobiSVD on the rows of a symmetric n x n matrix (App. B.4): returns the rotated rows
+// normalised (= rows of U^T) sorted by descending singular value.  Sign-defining for the PCA axes.
+__device__ void cv_jacobi_rows(double* A, double* w, int n) {
+  const double eps = 2.220446049250313e-16 * 10;
+  for (int i = 0; i < n; ++i) {
+    double sd = 0;
+    for (int k = 0; k < n; ++k) sd += A[i * n + k] * A[i * n + k];
+    w[i] = sd;
+  }
+  const int max_iter = n > 30 ? n : 30;
+  for (int iter = 0; iter < max_iter; ++iter) {
+    bool changed = false;
+    for (int i = 0; i < n - 1; ++i)
+      for (int j = i + 1; j < n; ++j) {
+        double* Ai = A + i * n;
+        double* Aj = A + j * n;
+        const double a = w[i], b = w[j];
+        double p = 0;
+        for (int k = 0; k < n; ++k) p += Ai[k] * Aj[k];
+        if (fabs(p) <= eps * sqrt(a * b)) continue;
+        p *= 2;
+        const double beta = a - b, gamma = hypot(p, beta);
+        double c, s;
+        if (beta < 0) {
+          const double delta = (gamma - beta) * 0.5;
+          s = sqrt(delta / gamma);
+          c = p / (gamma * s * 2);
+        } else {
+          c = sqrt((gamma + beta) / (gamma * 2));
+          s = p / (gamma * c * 2);
+        }
+        double na = 0, nb = 0;
+        for (int k = 0; k < n; ++k) {
+          const double t0 = c * Ai[k] + s * Aj[k];
+          const double t1 = -s * Ai[k] + c * Aj[k];
+          Ai[k] = t0;
+          Aj[k] = t1;
+          na += t0 * t0;
+          nb += t1 * t1;
+        }
+        w[i] = na;
+        w[j] = nb;
+        changed = true;
+      }
+    if (!changed) break;
+  }
+  for (int i = 0; i < n; ++i) {
+    double sd = 0;
+    for (int k = 0; k < n; ++k) sd += A[i * n + k] * A[i * n + k];
+    w[i] = sqrt(sd);
+  }
+  for (int i = 0; i < n - 1; ++i) {
+    int j = i;
+    for (int k = i + 1; k < n; ++k)
+      if (w[j] < w[k]) j = k;
+    if (i != j) {
+      const double tw = w[i];
+      w[i] = w[j];
+      w[j] = tw;
+      for (int k = 0; k < n; ++k) {
+        const double ta = A[i * n + k];
+        A[i * n + k] = A[j * n + k];
+        A[j * n + k] = ta;
+      }
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    const double s = w[i] > 2.2250738585072014e-308 ? 1.0 / w[i] : 0.0;
+    for (int k = 0; k < n; ++k) A[i * n + k] *= s;
+  }
+}
+
+// RANSACUpdateNumIters (App. B.6)
+__device__ int update_num_iters(double p, double ep, int max_iters) {
+  p = fmin(fmax(p, 0.0), 1.0);
+  ep = fmin(fmax(ep, 0.0), 1.0);
+  double num = fmax(1.0 - p, 2.2250738585072014e-308);
+  double denom = 1.0 - pow(1.0 - ep, (double)kModelPoints);
+  if (denom < 2.2250738585072014e-308) return 0;
+  num = log(num);
+  denom = log(denom);
+  return (denom >= 0 || -num >= max_iters * (-denom)) ? max_iters : (int)rint(num / denom);
+}
+
+// EPnP on n points in float64, OpenCV's sequence (epnp::compute_pose).
+__device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], const Camera& cam, double (&Rbest)[3][3],
+                         double (&tbest)[3]) {
+  const double fu = cam.fx, fv = cam.fy, uc = cam.cx, vc = cam.cy;
+  double us[kMaxLandmarks][2], al[kMaxLandmarks][4];
+  for (int i = 0; i < n; ++i) {
+    us[i][0] = und[i][0] * fu + uc;
+    us[i][1] = und[i][1] * fv + vc;
+  }
+  // control points: centroid + PCA axes from OpenCV's Jacobi (signs matter)
+  double cws[4][3] = {};
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < 3; ++c) cws[0][c] += pw[i][c];
+  for (int c = 0; c < 3; ++c) cws[0][c] /= n;
+  double cov[9] = {}, dc[3];
+  for (int i = 0; i < n; ++i) {
+    const double q[3] = {pw[i][0] - cws[0][0], pw[i][1] - cws[0][1], pw[i][2] - cws[0][2]};
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) cov[3 * r + c] += q[r] * q[c];
+  }
+  cv_jacobi_rows(cov, dc, 3);  // cov now holds uct
+  double inv_k[3];
+  for (int i = 0; i < 3; ++i) {
+    const double k = sqrt(dc[i] / n);
+    inv_k[i] = k > 0 ? 1.0 / k : 0.0;
+    for (int c = 0; c < 3; ++c) cws[i + 1][c] = cws[0][c] + k * cov[3 * i + c];
+  }
+  // barycentric coordinates: CC = [k_i u_i] has orthogonal columns, so CC^-1 = diag(1/k) U^T
+  for (int i = 0; i < n; ++i) {
+    const double q[3] = {pw[i][0] - cws[0][0], pw[i][1] - cws[0][1], pw[i][2] - cws[0][2]};
+    for (int j = 0; j < 3; ++j) al[i][1 + j] = (cov[3 * j] * q[0] + cov[3 * j + 1] * q[1] + cov[3 * j + 2] * q[2]) * inv_k[j];
+    al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
+  }
+  // MtM (12x12), accumulated row pair by row pair
+  double mtm[144] = {}, dw[12];
+  for (int i = 0; i < n; ++i) {
+    double r1[12], r2[12];
+    for (int j = 0; j < 4; ++j) {
+      r1[3 * j] = al[i][j] * fu, r1[3 * j + 1] = 0.0, r1[3 * j + 2] = al[i][j] * (uc - us[i][0]);
+      r2[3 * j] = 0.0, r2[3 * j + 1] = al[i][j] * fv, r2[3 * j + 2] = al[i][j] * (vc - us[i][1]);
+    }
+    for (int r = 0; r < 12; ++r)
+      for (int c = 0; c < 12; ++c) mtm[12 * r + c] += r1[r] * r1[c] + r2[r] * r2[c];
+  }
+  cv_jacobi_rows(mtm, dw, 12);  // rows of mtm are now ut
+  double v[4][12];
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 12; ++j) v[i][j] = mtm[12 * (11 - i) + j];
+  double L[6][10], rho[6];
+  build_L<double>(v, L);
+  build_rho<double>(cws, rho);
+
+  double pw0[3] = {};
+  for (int i = 0; i < n; ++i)
+    for (int c = 0; c < 3; ++c) pw0[c] += pw[i][c];
+  for (int c = 0; c < 3; ++c) pw0[c] /= n;
+
+  double best_err = 0.0;
+  for (int variant = 1; variant <= 3; ++variant) {
+    double be[4];
+    approx_betas<double>(L, rho, variant, be);
+    gauss_newton<double>(L, rho, be);
+    double ccs[4][3];
+    for (int j = 0; j < 4; ++j)
+      for (int c = 0; c < 3; ++c) ccs[j][c] = be[0] * v[0][3 * j + c] + be[1] * v[1][3 * j + c] + be[2] * v[2][3 * j + c] + be[3] * v[3][3 * j + c];
+    // sign from the first point's depth
+    double z0 = 0;
+    for (int j = 0; j < 4; ++j) z0 += al[0][j] * ccs[j][2];
+    const double sgn = z0 < 0 ? -1.0 : 1.0;
+    double pc0[3] = {};
+    for (int i = 0; i < n; ++i)
+      for (int c = 0; c < 3; ++c) pc0[c] += sgn * (al[i][0] * ccs[0][c] + al[i][1] * ccs[1][c] + al[i][2] * ccs[2][c] + al[i][3] * ccs[3][c]);
+    for (int c = 0; c < 3; ++c) pc0[c] /= n;
+    double abt[3][3] = {};
+    for (int i = 0; i < n; ++i) {
+      double pc[3];
+      for (int c = 0; c < 3; ++c) pc[c] = sgn * (al[i][0] * ccs[0][c] + al[i][1] * ccs[1][c] + al[i][2] * ccs[2][c] + al[i][3] * ccs[3][c]);
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) abt[r][c] += (pc[r] - pc0[r]) * (pw[i][c] - pw0[c]);
+    }
+    double R[3][3], t[3];
+    procrustes_uvt<double>(abt, R);
+    for (int r = 0; r < 3; ++r) t[r] = pc0[r] - (R[r][0] * pw0[0] + R[r][1] * pw0[1] + R[r][2] * pw0[2]);
+    double sum = 0;
+    for (int i = 0; i < n; ++i) {
+      const double Xc = R[0][0] * pw[i][0] + R[0][1] * pw[i][1] + R[0][2] * pw[i][2] + t[0];
+      const double Yc = R[1][0] * pw[i][0] + R[1][1] * pw[i][1] + R[1][2] * pw[i][2] + t[1];
+      const double iz = 1.0 / (R[2][0] * pw[i][0] + R[2][1] * pw[i][1] + R[2][2] * pw[i][2] + t[2]);
+      const double du = us[i][0] - (uc + fu * Xc * iz), dv = us[i][1] - (vc + fv * Yc * iz);
+      sum += sqrt(du * du + dv * dv);
+    }
+    const double err = sum / n;
+    // N = 1; if (err2 < err1) N = 2; if (err3 < err[N]) N = 3
+    if (variant == 1 || err < best_err) {
+      best_err = err;
+      for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Rbest[r][c] = R[r][c];
+        tbest[r] = t[r];
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const int n = ws.n[b];
+  const unsigned vis = ws.vis[b];
+  int status = SPE_FRAME_OK, winner = -1;
+  unsigned inl = 0;
+  if (n < 4) {
+    status = SPE_FRAME_TOO_FEW_POINTS;
+  } else if (n == 4) {
+    status = SPE_FRAME_P3P_UNSUPPORTED;
+  } else if (n == kModelPoints) {
+    inl = vis;  // cv2: model_points == npoints -> plain solvePnP, every point an inlier
+    winner = 0;
+  } else {
+    // sequential acceptance over the inlier counts (App. B.6)
+    const uint8_t* counts = ws.counts + (size_t)b * a.H;
+    int niters = a.H, max_good = 0;
+    for (int h = 0; h < niters; ++h) {
+      const int g = counts[h];
+      if (g > max(max_good, kModelPoints - 1)) {
+        winner = h;
+        max_good = g;
+        niters = update_num_iters(a.confidence, (double)(n - g) / n, niters);
+      }
+    }
+    if (winner < 0) status = SPE_FRAME_NO_MODEL;
+    else inl = ws.masks[(size_t)b * a.H + winner];
+  }
+  double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3] = {0, 0, 0};
+  if (status == SPE_FRAME_OK) {
+    double pw[kMaxLandmarks][3], und[kMaxLandmarks][2];
+    int k = 0;
+    for (int j = 0; j < m.J; ++j)
+      if ((inl >> j) & 1u) {
+        for (int c = 0; c < 3; ++c) pw[k][c] = (double)m.landmarks[3 * j + c];
+        const double2 q = ws.und[(size_t)b * m.J + j];
+        // RANSAC's final solve converts the image points to float64 before undistorting; the
+        // n == 5 shortcut hands cv2.solvePnP the float32 points, whose undistortion stays float32
+        und[k][0] = n == kModelPoints ? (double)(float)q.x : q.x;
+        und[k][1] = n == kModelPoints ? (double)(float)q.y : q.y;
+        ++k;
+      }
+    epnp_f64(k, pw, und, m.cam, R, t);
+  }
+  double q[4] = {1, 0, 0, 0};
+  if (status == SPE_FRAME_OK) rotation_to_quat(R, q);
+  float* o = a.pose7 + (size_t)b * 7;
+  const bool ok = status == SPE_FRAME_OK;
+  for (int i = 0; i < 4; ++i) o[i] = ok ? (float)q[i] : 0.f;
+  for (int i = 0; i < 3; ++i) o[4 + i] = ok ? (float)t[i] : 0.f;
+  a.inlier_mask[b] = inl;
+  a.status[b] = status;
+  if (a.winner) a.winner[b] = winner;
+  if (a.rt) {
+    double* r = a.rt + (size_t)b * 12;
+    for (int i = 0; i < 9; ++i) r[i] = ok ? R[i / 3][i % 3] : 0.0;
+    for (int i = 0; i < 3; ++i) r[9 + i] = ok ? t[i] : 0.0;
+  }
+}
+
+__global__ void debug_scores_kernel(RansacWorkspace ws, long long total, int32_t* counts, uint32_t* masks) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (counts) counts[i] = ws.counts[i];
+  if (masks) masks[i] = ws.masks[i];
+}
+
+}  // namespace
+
+cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
+  if (a.B == 0) return cudaSuccess;
+  DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam};
+  const int wpb = 4;
+  frame_prep_kernel<<<(a.B + wpb - 1) / wpb, wpb * 32, 0, stream>>>(dm, a.kpts, a.B, a.conf_floor, ws);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (m.J > kModelPoints) {
+    const int hblocks = (a.H + kHypPerCta - 1) / kHypPerCta;
+    const long long ctas = (long long)a.B * hblocks;
+    if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+    hypothesis_kernel<<<(unsigned)ctas, kHypPerCta * kGroup, 0, stream>>>(dm, a.kpts, a.H, hblocks, a.reproj_err * a.reproj_err,
+                                                                          a.jacobi_sweeps, ws);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  select_refit_kernel<<<(a.B + 31) / 32, 32, 0, stream>>>(dm, a, ws);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_debug_scores(const RansacWorkspace& ws, int B, int H, int32_t* counts, uint32_t* masks, cudaStream_t stream) {
+  const long long total = (long long)B * H;
+  if (total == 0) return cudaSuccess;
+  debug_scores_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(ws, total, counts, masks);
+  return cudaGetLastError();
+}
+
+}  // namespace spe

@@ -59,7 +59,7 @@ def _declare(L):
         L.spe_ransac_epnp_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_double, c_float, fp, up, ip, ip, dp,
                                           c_void_p, c_size_t, c_void_p]
         L.spe_ransac_debug_scores.restype = c_int
-        L.spe_ransac_debug_scores.argtypes = [c_void_p, c_int, c_int, ip, up, c_void_p]
+        L.spe_ransac_debug_scores.argtypes = [c_void_p, c_void_p, c_int, c_int, ip, up, c_void_p]
         L.spe_pipeline_workspace_bytes.restype = c_size_t
         L.spe_pipeline_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int]
         L.spe_heatmap_to_pose_f32.restype = c_int
