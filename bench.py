@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Benchmark of the heatmap -> 6-DoF pose stage (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (one process per GPU under torchrun for N > 1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): SPEED+ Tango, 11 landmarks, 64x64 heatmaps, 4096 frames per
+GPU per step, 256 RANSAC-EPnP hypotheses.  One step = decode + pose solve of one 4096-frame batch
+per rank (weak scaling) + the final all_gather of the [N,7] poses.  Heatmaps are 738 MB per rank,
+i.e. larger than the 126 MB L2, and are resident in HBM when the timed region starts (`value`);
+`e2e` repeats the measurement through the public host-buffer call (HeatmapToPose.run_host) with
+the host->device and device->host copies inside the timed region.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "spacecraft-pose-estimation_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frames/sec heatmap->6-DoF pose (decode + 256-hypothesis RANSAC-EPnP)"
+UNIT = "frames/s"
+FRAMES_PER_GPU = 4096
+J, HM_H, HM_W = 11, 64, 64
+HYPOTHESES = 256
+REPROJ = 15.0
+WORKLOAD = "SPEED+ Tango 11 landmarks, 64x64 heatmaps, batch 4096 per GPU, 256 RANSAC-EPnP hypotheses (BASELINE.json configs[1])"
+# SURVEY §8(d) algorithmic work
+DECODE_BYTES_PER_FRAME = J * HM_H * HM_W * 4 + J * 12 + 16
+HYP_FLOPS = 126_400 + 54 * J  # canonical FP32 flops per hypothesis at n = J
+
+
+def config_dict(n_gpus):
+    return {"workload": WORKLOAD, "frames_per_gpu_per_step": FRAMES_PER_GPU, "landmarks": J, "heatmap": [HM_H, HM_W],
+            "hypotheses": HYPOTHESES, "reprojection_error_px": REPROJ, "parallelism": f"frames sharded over {n_gpus} GPU(s), final all_gather of [N,7]",
+            "l2_policy": "inputs (738 MB heatmaps per rank) are larger than the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampled DURING the timed region
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.samples = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            parts = [x.strip() for x in s.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_workload(seed_offset: int, frames: int):
+    from spe_b200 import models, synth
+
+    model = models.tango()
+    fr = synth.make_frames(model, frames, HM_H, HM_W, seed=synth.BASE_SEED + 1 + seed_offset)
+    return model, fr
+
+
+def cpu_reference_frames(args):
+    """The reference's CPU path on a slice of frames: get_final_preds (oracle restatement with the
+    reference's loop structure) + the per-frame cv2.solvePnPRansac loop."""
+    import cv2
+
+    from oracle import decode_ref, pnp_ref
+
+    hm, c, s, lm, K, dist, iters = args
+    cv2.setNumThreads(1)
+    preds, maxvals = decode_ref.get_final_preds(True, hm, c, s)
+    kpts = np.concatenate([preds, maxvals], -1)
+    out = np.zeros((hm.shape[0], 7))
+    for b in range(hm.shape[0]):
+        ok, p7, _, _, _ = pnp_ref.pose_from_keypoints(kpts[b], lm, K, dist, iterations=iters)
+        out[b] = p7
+    return out
+
+
+def run_cpu_baseline(model, fr, frames: int, workers: int, repeats: int = 1):
+    """Returns (frames/s, seconds) of the reference CPU path over `frames` frames with `workers` processes."""
+    frames = min(frames, fr.heatmaps.shape[0])
+    if workers <= 1:
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            cpu_reference_frames((fr.heatmaps[:frames], fr.center[:frames], fr.scale[:frames], model.landmarks, model.K, model.dist, 10000))
+        dt = (time.perf_counter() - t0) / repeats
+        return frames / dt, dt
+    import multiprocessing as mp
+
+    bounds = np.linspace(0, frames, workers + 1).astype(int)
+    jobs = [(fr.heatmaps[a:b], fr.center[a:b], fr.scale[a:b], model.landmarks, model.K, model.dist, 10000)
+            for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    with mp.get_context("fork").Pool(workers) as pool:
+        pool.map(cpu_reference_frames, jobs[:workers])  # warm the workers (imports, page-in)
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            pool.map(cpu_reference_frames, jobs)
+        dt = (time.perf_counter() - t0) / repeats
+    return frames / dt, dt
+
+
+# ------------------------------------------------------------------------------------------------
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    workers = max(1, min(cores, 64))
+    sample = 2048
+    model, fr = make_workload(0, sample)
+    import multiprocessing as mp
+
+    bounds = np.linspace(0, sample, workers + 1).astype(int)
+    jobs = [(fr.heatmaps[a:b], fr.center[a:b], fr.scale[a:b], model.landmarks, model.K, model.dist, 10000)
+            for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    times = []
+    with mp.get_context("fork").Pool(workers) as pool:
+        for _ in range(max(args.warmup, 1)):
+            pool.map(cpu_reference_frames, jobs)
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            pool.map(cpu_reference_frames, jobs)
+            times.append(time.perf_counter() - t0)
+    total = float(np.sum(times))
+    value = sample * args.steps / total
+    desc = (f"{sample}-frame sample of the workload per step, frames split over {workers} worker processes (cv2.setNumThreads(1) each); "
+            "decode = oracle restatement of get_final_preds with the reference's loops, pose = cv2.solvePnPRansac(EPNP, iterationsCount=10000, 15 px)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": desc},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def gpu_arm(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import spe_b200
+    from spe_b200 import _lib
+    from spe_b200.pipeline import HeatmapToPose, all_gather_rows
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    model, fr = make_workload(rank, FRAMES_PER_GPU)
+    stage = HeatmapToPose(model, hypotheses=HYPOTHESES, reproj_err=REPROJ, device=dev)
+    L = _lib.lib()
+    hm_host = torch.from_numpy(fr.heatmaps).pin_memory()
+    c_host = torch.from_numpy(fr.center).pin_memory()
+    s_host = torch.from_numpy(fr.scale).pin_memory()
+    hm = hm_host.to(dev)
+    c, s = c_host.to(dev), s_host.to(dev)
+    B = FRAMES_PER_GPU
+    n_total = B * world
+    kpts = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+    pose7 = torch.empty((B, 7), dtype=torch.float32, device=dev)
+    mask = torch.empty((B,), dtype=torch.int32, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    ws_bytes = int(L.spe_ransac_workspace_bytes(stage.solver.handle, B, HYPOTHESES))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step(ev=None):
+        """One pass of the hot path.  Same kernels as spe_heatmap_to_pose_f32, issued as its two
+        C-ABI halves so that CUDA events can bracket the decode kernel."""
+        if ev is not None:
+            ev[0].record(stream)
+        _lib.check(L.spe_decode_kpts_f32(hm.data_ptr(), B, J, HM_H, HM_W, c.data_ptr(), s.data_ptr(), 1, kpts.data_ptr(), None, stream.cuda_stream),
+                   "spe_decode_kpts_f32")
+        if ev is not None:
+            ev[1].record(stream)
+        _lib.check(L.spe_ransac_epnp_f32(stage.solver.handle, kpts.data_ptr(), B, HYPOTHESES, REPROJ, 0.99, -1.0, pose7.data_ptr(), mask.data_ptr(),
+                                         status.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream.cuda_stream), "spe_ransac_epnp_f32")
+        if ev is not None:
+            ev[2].record(stream)
+        return all_gather_rows(pose7, n_total)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        poses = step()
+    barrier()
+    events = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_begin.record(stream)
+    for k in range(args.steps):
+        poses = step(events[k])
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_begin.elapsed_time(t_end)
+    decode_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in events]))
+    solve_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in events]))
+    assert poses.shape == (n_total, 7)
+
+    # ---- end to end through the public host-buffer call (pinned inputs, copies inside the timed region)
+    for _ in range(2):
+        out = stage.run_host(hm_host, c_host, s_host, chunk=512)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = stage.run_host(hm_host, c_host, s_host, chunk=512)
+        all_gather_rows(torch.from_numpy(out.pose7).to(dev), n_total)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([ms_total, decode_ms, solve_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, decode_ms, solve_ms, e2e_ms = (float(x) for x in times.cpu())
+
+    # parity spot check inside the bench: the device poses of step K equal the host-call poses
+    same = bool(np.array_equal(out.pose7, pose7.cpu().numpy()))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json (measured copy bandwidth, burst)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        decode_gbs = B * DECODE_BYTES_PER_FRAME / (decode_ms * 1e-3) / 1e9
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_peak = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+        solver_tflops = B * HYPOTHESES * HYP_FLOPS / (solve_ms * 1e-3) / 1e12
+        value = n_total * args.steps / (ms_total * 1e-3)
+        cpu = None
+        if world == 1:
+            sample = 1024
+            v, secs = run_cpu_baseline(model, fr, sample, workers=1)
+            cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"first {sample} frames of the same batch, 1 thread: oracle get_final_preds (reference loop structure) + "
+                             f"cv2.solvePnPRansac(EPNP, iterationsCount=10000, 15 px) per frame; {secs:.1f} s"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": config_dict(world),
+            "e2e": {"value": n_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * (J * HM_H * HM_W * 4 + 16),
+                    "d2h_bytes_per_step": B * (28 + 4 + 4 + J * 12), "api": "HeatmapToPose.run_host (pinned host tensors, 512-frame chunks, 2 streams)"},
+            "gpu_launches": 4 * args.steps,
+            "roofline": {"bound": "hbm", "kernel": "decode_bulk_kernel", "achieved": decode_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": decode_gbs / hbm_peak, "traffic": 738.29e6 + 4.1e6, "traffic_note": "ncu dram read+write per launch, profiles/decode_r1.md",
+                         "peak_source": peak_src, "ms_per_launch": decode_ms, "algorithmic_bytes_per_launch": B * DECODE_BYTES_PER_FRAME},
+            "solver": {"bound": "fp32", "kernel": "hypothesis_kernel (+prep, select/refit)", "achieved": solver_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                       "frac": solver_tflops / fp32_peak, "ms_per_step": solve_ms, "flops_per_hypothesis": HYP_FLOPS,
+                       "peak_source": f"148 SMs x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz (nominal pipe width at the observed clock)"},
+            "clocks": clocks, "host_call_matches_device_call": same,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-launch one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
+               "--warmup", str(args.warmup)]
+        raise SystemExit(subprocess.call(cmd))
+    gpu_arm(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,185 @@
+"""Heatmaps -> 6-DoF poses without leaving the device, sharded by frames across ranks.
+
+The reference crosses a process and a file boundary between its two halves
+(`pred.mat`: lib/dataset/PEdataset.py:121-123 -> pose_estimation/export_predicted_poses_real.py:172-173).
+Here decode and pose solve run back to back on one stream through spe_heatmap_to_pose_f32
+(include/spe_b200.h); the keypoints ([B,J,3], the pred.mat row layout) stay in HBM and are returned
+so the rest of the reference pipeline can still write its files from them.
+
+Multi-GPU: frames are independent, so rank r owns the contiguous slice
+[r*N/G, (r+1)*N/G) and there is no collective in the hot loop; one all_gather of the [N/G,7]
+pose tensor (28 B/frame) at the end.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from .models import CameraModel
+from .pnp import ADAPTIVE_CONFIDENCE_FILTER, PnPSolver
+
+
+@dataclass
+class StageOutput:
+    pose7: object  # [B,7] float32 (qw,qx,qy,qz,tx,ty,tz)
+    inlier_mask: object  # [B] int32 (uint32 bits over the J landmarks)
+    status: object  # [B] int32 (pnp.FRAME_*)
+    kpts: object  # [B,J,3] float32 (x, y, maxval): what the reference stores in pred.mat
+
+
+def shard_bounds(n: int, world: int, rank: int):
+    """Contiguous, balanced partition of n frames: the first n % world ranks get one extra."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_rows(local, n_total: int, group=None):
+    """all_gather of row-sharded tensors produced with shard_bounds (uneven shards are padded to
+    the largest one for the collective and trimmed afterwards).  Works on NCCL (CUDA tensors) and
+    gloo (CPU tensors).  Returns the [n_total, ...] tensor on every rank."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    per = (n_total + world - 1) // world
+    pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    pieces = []
+    for r in range(world):
+        lo, hi = shard_bounds(n_total, world, r)
+        pieces.append(out[r * per: r * per + (hi - lo)])
+    return torch.cat(pieces, dim=0)
+
+
+class HeatmapToPose:
+    """The whole stage for one landmark/camera model on one GPU."""
+
+    def __init__(self, model: CameraModel, hypotheses: int = 256, reproj_err: float = 15.0, confidence: float = 0.99,
+                 conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, post_process: bool = True, device=None):
+        torch = _lib.require_cuda()
+        self.model = model
+        self.hypotheses = int(hypotheses)
+        self.reproj_err = float(reproj_err)
+        self.confidence = float(confidence)
+        self.conf_floor = float(conf_floor)
+        self.post_process = bool(post_process)
+        self.solver = PnPSolver(model.landmarks, model.K, model.dist, max_hypotheses=self.hypotheses, device=device)
+        self.device = self.solver.device
+        self._L = _lib.lib()
+        self._ws = None
+        self._torch = torch
+
+    def _workspace(self, B: int):
+        need = int(self._L.spe_pipeline_workspace_bytes(self.solver.handle, B, self.solver.J, self.hypotheses))
+        if need == 0:
+            raise _lib.SpeError("spe_pipeline_workspace_bytes rejected the configuration")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = self._torch.empty(need, dtype=self._torch.uint8, device=self.device)
+        return self._ws
+
+    def run_device(self, hm, center, scale, out: StageOutput | None = None) -> StageOutput:
+        """hm [B,J,H,W], center/scale [B,2]: float32 CUDA contiguous.  Enqueues decode + prep +
+        hypotheses + selection/refit on torch's current stream; no host synchronisation."""
+        torch = self._torch
+        B, J, H, W = hm.shape
+        assert hm.is_cuda and hm.dtype == torch.float32 and hm.is_contiguous() and J == self.solver.J
+        dev = hm.device
+        if out is None:
+            out = StageOutput(torch.empty((B, 7), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+                              torch.empty((B,), dtype=torch.int32, device=dev), torch.empty((B, J, 3), dtype=torch.float32, device=dev))
+        ws = self._workspace(B)
+        with torch.cuda.device(dev):
+            _lib.check(self._L.spe_heatmap_to_pose_f32(
+                self.solver.handle, hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(self.post_process),
+                self.hypotheses, self.reproj_err, self.confidence, self.conf_floor, out.pose7.data_ptr(), out.inlier_mask.data_ptr(),
+                out.status.data_ptr(), out.kpts.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream),
+                "spe_heatmap_to_pose_f32")
+        return out
+
+    def run_host(self, heatmaps, center, scale, chunk: int = 1024) -> StageOutput:
+        """Host buffers in, host buffers out: the call a user of the reference would make with
+        the arrays it already has (`output.cpu().numpy()`, meta['center'], meta['scale']).
+
+        Frames stream through the GPU in chunks on two streams so the host->device copy of chunk
+        i+1 overlaps the kernels of chunk i; pinned inputs (torch CPU tensors with pin_memory, or
+        NumPy views of them) are copied asynchronously, pageable ones go through the driver's
+        staging path.  Returns NumPy arrays.
+        """
+        torch = self._torch
+        hm = torch.from_numpy(heatmaps) if isinstance(heatmaps, np.ndarray) else heatmaps
+        c = torch.from_numpy(np.ascontiguousarray(center, np.float32)) if not isinstance(center, torch.Tensor) else center
+        s = torch.from_numpy(np.ascontiguousarray(scale, np.float32)) if not isinstance(scale, torch.Tensor) else scale
+        assert hm.ndim == 4, "batch_images should be 4-ndim"
+        hm = hm.contiguous().float()
+        N, J, H, W = hm.shape
+        dev = self.device
+        chunk = max(1, min(int(chunk), N))
+        copy_stream, run_stream = self._streams()
+        bufs = self._staging(chunk, J, H, W)
+        pose7 = torch.empty((N, 7), dtype=torch.float32).pin_memory()
+        mask = torch.empty((N,), dtype=torch.int32).pin_memory()
+        status = torch.empty((N,), dtype=torch.int32).pin_memory()
+        kpts = torch.empty((N, J, 3), dtype=torch.float32).pin_memory()
+        for i, lo in enumerate(range(0, N, chunk)):
+            hi = min(N, lo + chunk)
+            b = hi - lo
+            buf = bufs[i % len(bufs)]
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(buf["free"])  # the kernels that last read this buffer are done
+                buf["hm"][:b].copy_(hm[lo:hi], non_blocking=True)
+                buf["c"][:b].copy_(c[lo:hi], non_blocking=True)
+                buf["s"][:b].copy_(s[lo:hi], non_blocking=True)
+                buf["ready"].record(copy_stream)
+            with torch.cuda.stream(run_stream):
+                run_stream.wait_event(buf["ready"])
+                out = StageOutput(buf["pose7"][:b], buf["mask"][:b], buf["status"][:b], buf["kpts"][:b])
+                self.run_device(buf["hm"][:b], buf["c"][:b], buf["s"][:b], out)
+                pose7[lo:hi].copy_(out.pose7, non_blocking=True)
+                mask[lo:hi].copy_(out.inlier_mask, non_blocking=True)
+                status[lo:hi].copy_(out.status, non_blocking=True)
+                kpts[lo:hi].copy_(out.kpts, non_blocking=True)
+                buf["free"].record(run_stream)
+        run_stream.synchronize()
+        return StageOutput(pose7.numpy(), mask.numpy(), status.numpy(), kpts.numpy())
+
+    def __call__(self, heatmaps, center, scale):
+        torch = self._torch
+        if isinstance(heatmaps, torch.Tensor) and heatmaps.is_cuda:
+            return self.run_device(heatmaps.contiguous().float(), center.to(heatmaps.device).contiguous().float(),
+                                   scale.to(heatmaps.device).contiguous().float())
+        return self.run_host(heatmaps, center, scale)
+
+    # -- internals
+    def _streams(self):
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = self._torch.cuda.Stream(self.device)
+            self._run_stream = self._torch.cuda.Stream(self.device)
+        return self._copy_stream, self._run_stream
+
+    def _staging(self, chunk, J, H, W, depth: int = 3):
+        torch = self._torch
+        key = (chunk, J, H, W)
+        if getattr(self, "_staging_key", None) != key:
+            self._bufs = []
+            for _ in range(depth):
+                ev_free, ev_ready = torch.cuda.Event(), torch.cuda.Event()
+                ev_free.record(torch.cuda.current_stream(self.device))
+                self._bufs.append({
+                    "hm": torch.empty((chunk, J, H, W), dtype=torch.float32, device=self.device),
+                    "c": torch.empty((chunk, 2), dtype=torch.float32, device=self.device),
+                    "s": torch.empty((chunk, 2), dtype=torch.float32, device=self.device),
+                    "pose7": torch.empty((chunk, 7), dtype=torch.float32, device=self.device),
+                    "mask": torch.empty((chunk,), dtype=torch.int32, device=self.device),
+                    "status": torch.empty((chunk,), dtype=torch.int32, device=self.device),
+                    "kpts": torch.empty((chunk, J, 3), dtype=torch.float32, device=self.device),
+                    "free": ev_free, "ready": ev_ready,
+                })
+            self._staging_key = key
+        return self._bufs
