@@ -45,6 +45,32 @@ __device__ __forceinline__ void jacobi_angle(T a, T b, T p, T& c, T& s, T& t) {
   s = c * t;
 }
 
+// FP32 variant on the SFU approximations (rcp/sqrt/rsqrt.approx, ~1 ulp): 4 MUFU + ~8 FP32 ops and
+// no slow-path branches.  A rotation only has to be orthogonal to rounding accuracy, which
+// c = rsqrt(1 + t^2), s = c t guarantees irrespective of how exact t is.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void jacobi_angle_fast(float a, float b, float p, float& c, float& s, float& t) {
+  const float zeta = (b - a) * rcp_approx(p + p);
+  const float q = fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.0f));  // zeta^2 = inf -> q = inf -> t = 0
+  t = copysignf(rcp_approx(q), zeta);
+  c = rsqrt_approx(fmaf(t, t, 1.0f));
+  s = c * t;
+}
+
 // Householder least squares min |A x - b| for a tiny R x C system held in registers.
 // Zero (masked) columns are skipped and get x = 0.  A and b are overwritten.
 template <typename T, int R, int C>

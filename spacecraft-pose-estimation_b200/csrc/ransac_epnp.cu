@@ -212,7 +212,7 @@ __device__ __forceinline__ void jacobi_sweeps(float (&Mr)[3][12], float (&Vr)[3]
         const int p = rr_p(r, k), q = rr_q(r, k);
         const bool rot = g[k] * g[k] > kTol2 * d[p] * d[q];
         float t;
-        jacobi_angle<float>(d[p], d[q], rot ? g[k] : 1.0f, c[k], s[k], t);
+        jacobi_angle_fast(d[p], d[q], rot ? g[k] : 1.0f, c[k], s[k], t);
         c[k] = rot ? c[k] : 1.0f;
         s[k] = rot ? s[k] : 0.0f;
         t = rot ? t : 0.0f;
@@ -267,7 +267,7 @@ __device__ __forceinline__ void control_points5(const float (&pw)[5][3], float (
       }
       const bool rot = g * g > 1.4e-14f * a * b;
       float c, s, t;
-      jacobi_angle<float>(a, b, rot ? g : 1.f, c, s, t);
+      jacobi_angle_fast(a, b, rot ? g : 1.f, c, s, t);
       c = rot ? c : 1.f;
       s = rot ? s : 0.f;
 #pragma unroll
