@@ -127,11 +127,20 @@ size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypothese
   return spe::ransac_workspace_bytes(model->m.J, B, hypotheses);
 }
 
+static int hyp_kernel_setting() {
+  static int variant = [] {
+    const char* v = getenv("SPE_HYP_KERNEL");  // dev knob: "g4" = 4 lanes per hypothesis
+    return (v && v[0] == 'g') ? 1 : 0;
+  }();
+  return variant;
+}
+
 static int jacobi_sweeps_setting() {
   static int sweeps = [] {
     const char* v = getenv("SPE_JACOBI_SWEEPS");  // dev knob
-    const int s = v ? atoi(v) : 6;
-    return s > 0 && s <= 30 ? s : 6;
+    const int dflt = hyp_kernel_setting() == 1 ? 5 : 6;
+    const int s = v ? atoi(v) : dflt;
+    return s > 0 && s <= 30 ? s : dflt;
   }();
   return sweeps;
 }
@@ -153,6 +162,7 @@ int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int 
   a.confidence = confidence;
   a.conf_floor = conf_floor;
   a.jacobi_sweeps = jacobi_sweeps_setting();
+  a.kernel_variant = hyp_kernel_setting();
   a.pose7 = pose7;
   a.inlier_mask = inlier_mask;
   a.status = status;

@@ -521,6 +521,340 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
 }
 
 // ------------------------------------------------------------------------------------------
+// 2b. hypothesis kernel, one THREAD per (frame, hypothesis)
+//
+// Same mathematics, different side of the SVD: instead of rotating the 12 columns of M (and
+// accumulating V), the 10 columns of M^T (12 x 10) are orthogonalised.  After convergence the
+// normalised columns ARE the right singular vectors of M with non-zero singular value (no
+// accumulator needed: 120 registers hold the whole problem), the two smallest give EPnP's v2, v3,
+// and the 2-D null space (v0, v1) is the orthogonal complement, built from two columns of the
+// projector I - sum v_i v_i^T.  45 pairs x 12 rows per sweep instead of 66 pairs x 22 rows, no
+// shuffles, no work replicated across lanes; the three beta variants run one after the other.
+constexpr int kT1Threads = 128;
+constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alphas[5][4] (+1: odd stride, conflict-free)
+
+__host__ __device__ constexpr int rr10_p(int r, int k) { return k == 0 ? r : (r + k) % 9; }
+__host__ __device__ constexpr int rr10_q(int r, int k) { return k == 0 ? 9 : (r - k + 9) % 9; }
+
+__device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], int sweeps) {
+  constexpr float kTol2 = 9e-14f;
+#pragma unroll 1
+  for (int sw = 0; sw < sweeps; ++sw) {
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < 12; r += 2) s0 = fmaf(A[r][j], A[r][j], s0), s1 = fmaf(A[r + 1][j], A[r + 1][j], s1);
+      d[j] = s0 + s1;
+    }
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      float g[5], c[5], s[5];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int p = rr10_p(r, k), q = rr10_q(r, k);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; i += 3) {
+          s0 = fmaf(A[i][p], A[i][q], s0);
+          s1 = fmaf(A[i + 1][p], A[i + 1][q], s1);
+          s2 = fmaf(A[i + 2][p], A[i + 2][q], s2);
+        }
+        g[k] = s0 + s1 + s2;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int p = rr10_p(r, k), q = rr10_q(r, k);
+        const bool rot = g[k] * g[k] > kTol2 * d[p] * d[q];
+        float t;
+        jacobi_angle_fast(d[p], d[q], rot ? g[k] : 1.0f, c[k], s[k], t);
+        c[k] = rot ? c[k] : 1.0f;
+        s[k] = rot ? s[k] : 0.0f;
+        t = rot ? t : 0.0f;
+        d[p] = fmaxf(d[p] - t * g[k], 0.0f);
+        d[q] = fmaxf(d[q] + t * g[k], 0.0f);
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int p = rr10_p(r, k), q = rr10_q(r, k);
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const float x = A[i][p], y = A[i][q];
+          A[i][p] = c[k] * x - s[k] * y;
+          A[i][q] = s[k] * x + c[k] * y;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 12; r += 2) s0 = fmaf(A[r][j], A[r][j], s0), s1 = fmaf(A[r + 1][j], A[r + 1][j], s1);
+    d[j] = s0 + s1;
+  }
+}
+
+__global__ void __launch_bounds__(kT1Threads, 3)
+hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblocks, float thr2, int sweeps, RansacWorkspace ws) {
+  __shared__ float s_pw[kMaxLandmarks][3];
+  __shared__ float2 s_us[kMaxLandmarks];
+  __shared__ float2 s_img[kMaxLandmarks];
+  __shared__ float s_work[kT1Threads][kT1Stride];
+
+  const int b = blockIdx.x / hblocks, hb = blockIdx.x - b * hblocks;
+  const int n = ws.n[b];
+  if (n <= kModelPoints) return;
+  const unsigned vis = ws.vis[b];
+  const int tid = threadIdx.x;
+  if (tid < n) {
+    const int j = __fns(vis, 0, tid + 1);
+    s_pw[tid][0] = m.landmarks[3 * j], s_pw[tid][1] = m.landmarks[3 * j + 1], s_pw[tid][2] = m.landmarks[3 * j + 2];
+    s_us[tid] = ws.us_hyp[(size_t)b * m.J + j];
+    const float* k = kpts + ((size_t)b * m.J + j) * 3;
+    s_img[tid] = make_float2(k[0], k[1]);
+  }
+  __syncthreads();
+
+  const int h = hb * kT1Threads + tid;
+  if (h >= H) return;
+  const uint8_t* sub = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
+  int si[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) si[k] = sub[k];
+  float* work = s_work[tid];
+  const float fu = (float)m.cam.fx, fv = (float)m.cam.fy, uc = (float)m.cam.cx, vc = (float)m.cam.cy;
+
+  // ---- control points, alphas, M^T ---------------------------------------------------------
+  float rho[6];
+  float A[12][10], d[10];
+  {
+    float pw[5][3], al[5][4], cws[4][3];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) pw[k][0] = s_pw[si[k]][0], pw[k][1] = s_pw[si[k]][1], pw[k][2] = s_pw[si[k]][2];
+    control_points5(pw, cws, al);
+    build_rho<float>(cws, rho);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float du = uc - s_us[si[k]].x, dv = vc - s_us[si[k]].y;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = al[k][j];
+        work[48 + 4 * k + j] = a;
+        A[3 * j][2 * k] = a * fu, A[3 * j + 1][2 * k] = 0.f, A[3 * j + 2][2 * k] = a * du;
+        A[3 * j][2 * k + 1] = 0.f, A[3 * j + 1][2 * k + 1] = a * fv, A[3 * j + 2][2 * k + 1] = a * dv;
+      }
+    }
+  }
+  jacobi_mt(A, d, sweeps);
+
+  // ---- v2, v3 = the two smallest singular directions; v0, v1 = null space (complement) ---------
+  {
+    int j2 = 0, j3 = 0;
+    float b2 = INFINITY, b3 = INFINITY;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const bool lt2 = d[j] < b2, lt3 = d[j] < b3;
+      j3 = lt2 ? j2 : (lt3 ? j : j3);
+      b3 = lt2 ? b2 : (lt3 ? d[j] : b3);
+      j2 = lt2 ? j : j2;
+      b2 = lt2 ? d[j] : b2;
+    }
+    float diag[12];
+#pragma unroll
+    for (int r = 0; r < 12; ++r) diag[r] = 1.0f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const float inv = rsqrt_approx(fmaxf(d[j], 1e-30f));
+      float v2r, v3r;
+#pragma unroll
+      for (int r = 0; r < 12; ++r) {
+        A[r][j] *= inv;
+        diag[r] = fmaf(-A[r][j], A[r][j], diag[r]);
+        v2r = A[r][j];
+        if (j == j2) work[24 + r] = v2r;
+        if (j == j3) work[36 + r] = v2r;
+      }
+      (void)v3r;
+    }
+    // first null vector: the projector column with the largest norm
+    float n0[12], n1[12];
+    {
+      int a = 0;
+      float best = diag[0];
+#pragma unroll
+      for (int r = 1; r < 12; ++r) {
+        const bool gt = diag[r] > best;
+        best = gt ? diag[r] : best;
+        a = gt ? r : a;
+      }
+#pragma unroll
+      for (int r = 0; r < 12; ++r) n0[r] = r == a ? 1.0f : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        float coef = 0.f;
+#pragma unroll
+        for (int r = 0; r < 12; ++r) coef = r == a ? A[r][j] : coef;
+#pragma unroll
+        for (int r = 0; r < 12; ++r) n0[r] = fmaf(-coef, A[r][j], n0[r]);
+      }
+      float nn = 0.f;
+#pragma unroll
+      for (int r = 0; r < 12; ++r) nn = fmaf(n0[r], n0[r], nn);
+      const float inv = rsqrt_approx(fmaxf(nn, 1e-30f));
+#pragma unroll
+      for (int r = 0; r < 12; ++r) n0[r] *= inv;
+    }
+    {
+      int bsel = 0;
+      float best = -1.f;
+#pragma unroll
+      for (int r = 0; r < 12; ++r) {
+        const float res = diag[r] - n0[r] * n0[r];
+        const bool gt = res > best;
+        best = gt ? res : best;
+        bsel = gt ? r : bsel;
+      }
+#pragma unroll
+      for (int r = 0; r < 12; ++r) n1[r] = r == bsel ? 1.0f : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        float coef = 0.f;
+#pragma unroll
+        for (int r = 0; r < 12; ++r) coef = r == bsel ? A[r][j] : coef;
+#pragma unroll
+        for (int r = 0; r < 12; ++r) n1[r] = fmaf(-coef, A[r][j], n1[r]);
+      }
+      float dot = 0.f;
+#pragma unroll
+      for (int r = 0; r < 12; ++r) dot = fmaf(n1[r], n0[r], dot);
+      float nn = 0.f;
+#pragma unroll
+      for (int r = 0; r < 12; ++r) {
+        n1[r] = fmaf(-dot, n0[r], n1[r]);
+        nn = fmaf(n1[r], n1[r], nn);
+      }
+      const float inv = rsqrt_approx(fmaxf(nn, 1e-30f));
+#pragma unroll
+      for (int r = 0; r < 12; ++r) n1[r] *= inv;
+    }
+#pragma unroll
+    for (int r = 0; r < 12; ++r) work[r] = n0[r], work[12 + r] = n1[r];
+  }
+
+  // ---- the three beta variants, one after the other; keep the best by OpenCV's rule -----------
+  float Rb[3][3], tb[3], eb = 0.f;
+  {
+    float L[6][10];
+    {
+      float v[4][12];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 12; ++j) v[i][j] = work[12 * i + j];
+      build_L<float>(v, L);
+    }
+    float pw[5][3], pw0[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        pw[k][c] = s_pw[si[k]][c];
+        pw0[c] += pw[k][c];
+      }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pw0[c] *= 0.2f;
+#pragma unroll 1
+    for (int variant = 1; variant <= 3; ++variant) {
+      float betas[4];
+      approx_betas<float>(L, rho, variant, betas);
+      gauss_newton<float>(L, rho, betas);
+      float ccs[4][3];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          ccs[j][c] = betas[0] * work[3 * j + c] + betas[1] * work[12 + 3 * j + c] + betas[2] * work[24 + 3 * j + c] +
+                      betas[3] * work[36 + 3 * j + c];
+      float pcs[5][3];
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          pcs[k][c] = work[48 + 4 * k] * ccs[0][c] + work[48 + 4 * k + 1] * ccs[1][c] + work[48 + 4 * k + 2] * ccs[2][c] +
+                      work[48 + 4 * k + 3] * ccs[3][c];
+      const float sgn = pcs[0][2] < 0.f ? -1.f : 1.f;
+      float pc0[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          pcs[k][c] *= sgn;
+          pc0[c] += pcs[k][c];
+        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pc0[c] *= 0.2f;
+      float abt[3][3] = {};
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) abt[r][c] = fmaf(pcs[k][r] - pc0[r], pw[k][c] - pw0[c], abt[r][c]);
+      float R[3][3], t[3];
+      procrustes_uvt<float>(abt, R);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) t[r] = pc0[r] - (R[r][0] * pw0[0] + R[r][1] * pw0[1] + R[r][2] * pw0[2]);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float Xc = R[0][0] * pw[k][0] + R[0][1] * pw[k][1] + R[0][2] * pw[k][2] + t[0];
+        const float Yc = R[1][0] * pw[k][0] + R[1][1] * pw[k][1] + R[1][2] * pw[k][2] + t[1];
+        const float iz = 1.0f / (R[2][0] * pw[k][0] + R[2][1] * pw[k][1] + R[2][2] * pw[k][2] + t[2]);
+        const float du = s_us[si[k]].x - (uc + fu * Xc * iz), dv = s_us[si[k]].y - (vc + fv * Yc * iz);
+        sum += sqrtf(du * du + dv * dv);
+      }
+      const float err = sum * 0.2f;
+      if (variant == 1 || err < eb) {  // N = 1; if (e2 < e1) N = 2; if (e3 < e[N]) N = 3
+        eb = err;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Rb[r][c] = R[r][c];
+          tb[r] = t[r];
+        }
+      }
+    }
+  }
+
+  // ---- score all n points ------------------------------------------------------------------
+  unsigned bits = 0;
+  {
+    const float k1 = (float)m.cam.k1, k2 = (float)m.cam.k2, p1 = (float)m.cam.p1, p2 = (float)m.cam.p2, k3 = (float)m.cam.k3;
+    unsigned rest = vis;
+    for (int k = 0; k < n; ++k) {
+      const int j = __ffs(rest) - 1;  // landmark number of the k-th visible point
+      rest &= rest - 1;
+      const float X = s_pw[k][0], Y = s_pw[k][1], Z = s_pw[k][2];
+      const float xc = Rb[0][0] * X + Rb[0][1] * Y + Rb[0][2] * Z + tb[0];
+      const float yc = Rb[1][0] * X + Rb[1][1] * Y + Rb[1][2] * Z + tb[1];
+      const float zc = Rb[2][0] * X + Rb[2][1] * Y + Rb[2][2] * Z + tb[2];
+      const float iz = 1.0f / zc;
+      const float x = xc * iz, y = yc * iz;
+      const float r2 = x * x + y * y;
+      const float cd = 1.0f + ((k3 * r2 + k2) * r2 + k1) * r2;
+      const float xd = x * cd + 2.0f * p1 * x * y + p2 * (r2 + 2.0f * x * x);
+      const float yd = y * cd + p1 * (r2 + 2.0f * y * y) + 2.0f * p2 * x * y;
+      const float du = s_img[k].x - (fu * xd + uc), dv = s_img[k].y - (fv * yd + vc);
+      const float e = du * du + dv * dv;
+      if (e <= thr2) bits |= 1u << j;
+    }
+  }
+  ws.masks[(size_t)b * H + h] = bits;
+  ws.counts[(size_t)b * H + h] = (uint8_t)__popc(bits);
+}
+
+// ------------------------------------------------------------------------------------------
 // 3. selection + final refit (float64, one thread per frame)
 
 // OpenCV's JacobiSVD on the rows of a symmetric n x n matrix (App. B.4): returns the rotated rows
@@ -788,11 +1122,18 @@ cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const Ransac
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (m.J > kModelPoints) {
-    const int hblocks = (a.H + kHypPerCta - 1) / kHypPerCta;
-    const long long ctas = (long long)a.B * hblocks;
-    if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
-    hypothesis_kernel<<<(unsigned)ctas, kHypPerCta * kGroup, 0, stream>>>(dm, a.kpts, a.H, hblocks, a.reproj_err * a.reproj_err,
-                                                                          a.jacobi_sweeps, ws);
+    const float thr2 = a.reproj_err * a.reproj_err;
+    if (a.kernel_variant == 1) {  // 4 lanes per hypothesis (kept for A/B measurements)
+      const int hblocks = (a.H + kHypPerCta - 1) / kHypPerCta;
+      const long long ctas = (long long)a.B * hblocks;
+      if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+      hypothesis_kernel<<<(unsigned)ctas, kHypPerCta * kGroup, 0, stream>>>(dm, a.kpts, a.H, hblocks, thr2, a.jacobi_sweeps, ws);
+    } else {  // one thread per hypothesis
+      const int hblocks = (a.H + kT1Threads - 1) / kT1Threads;
+      const long long ctas = (long long)a.B * hblocks;
+      if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+      hypothesis_kernel_t1<<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, hblocks, thr2, a.jacobi_sweeps, ws);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
