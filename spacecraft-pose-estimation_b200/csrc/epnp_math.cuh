@@ -10,14 +10,33 @@
 
 namespace spe {
 
+// SFU approximations (rcp/sqrt/rsqrt.approx.ftz, ~1 ulp, no slow-path branches).  The FP32 path
+// only scores hypotheses against a 15 px threshold; the one result that is returned to the caller
+// is refit in float64.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rsqrt_approx(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 template <typename T>
 struct Real;
 template <>
 struct Real<float> {
-  static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
-  static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+  static __device__ __forceinline__ float sqrt(float x) { return sqrt_approx(x); }
+  static __device__ __forceinline__ float rsqrt(float x) { return rsqrt_approx(x); }
   static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
-  static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+  static __device__ __forceinline__ float rcp(float x) { return rcp_approx(x); }
+  static __device__ __forceinline__ float div(float a, float b) { return a * rcp_approx(b); }
   static __device__ __forceinline__ float copysign(float m, float s) { return copysignf(m, s); }
   static constexpr float eps = 1.1920929e-7f;
   static constexpr float tiny = 1e-30f;
@@ -29,6 +48,7 @@ struct Real<double> {
   static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   static __device__ __forceinline__ double abs(double x) { return fabs(x); }
   static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
   static __device__ __forceinline__ double copysign(double m, double s) { return ::copysign(m, s); }
   static constexpr double eps = 2.220446049250313e-16;
   static constexpr double tiny = 1e-280;
@@ -45,30 +65,18 @@ __device__ __forceinline__ void jacobi_angle(T a, T b, T p, T& c, T& s, T& t) {
   s = c * t;
 }
 
-// FP32 variant on the SFU approximations (rcp/sqrt/rsqrt.approx, ~1 ulp): 4 MUFU + ~8 FP32 ops and
-// no slow-path branches.  A rotation only has to be orthogonal to rounding accuracy, which
+// FP32: 4 MUFU + ~8 FP32 ops.  A rotation only has to be orthogonal to rounding accuracy, which
 // c = rsqrt(1 + t^2), s = c t guarantees irrespective of how exact t is.
-__device__ __forceinline__ float rcp_approx(float x) {
-  float r;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ float rsqrt_approx(float x) {
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ void jacobi_angle_fast(float a, float b, float p, float& c, float& s, float& t) {
   const float zeta = (b - a) * rcp_approx(p + p);
   const float q = fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.0f));  // zeta^2 = inf -> q = inf -> t = 0
   t = copysignf(rcp_approx(q), zeta);
   c = rsqrt_approx(fmaf(t, t, 1.0f));
   s = c * t;
+}
+template <>
+__device__ __forceinline__ void jacobi_angle<float>(float a, float b, float p, float& c, float& s, float& t) {
+  jacobi_angle_fast(a, b, p, c, s, t);
 }
 
 // Householder least squares min |A x - b| for a tiny R x C system held in registers.
@@ -86,7 +94,7 @@ __device__ __forceinline__ void lsq_householder(T (&A)[R][C], T (&b)[R], T (&x)[
     const T alpha = akk > T(0) ? -norm : norm;  // R_kk
     const T vk = akk - alpha;
     const T denom = -alpha * vk;  // = v^T v / 2  (>= norm^2)
-    const T inv = denom > Real<T>::tiny ? T(1) / denom : T(0);
+    const T inv = denom > Real<T>::tiny ? Real<T>::rcp(denom) : T(0);
     A[k][k] = vk;
 #pragma unroll
     for (int j = k + 1; j < C; ++j) {
@@ -110,7 +118,7 @@ __device__ __forceinline__ void lsq_householder(T (&A)[R][C], T (&b)[R], T (&x)[
     T acc = b[k];
 #pragma unroll
     for (int j = k + 1; j < C; ++j) acc -= A[k][j] * x[j];
-    x[k] = Real<T>::abs(diag[k]) > Real<T>::tiny ? acc / diag[k] : T(0);
+    x[k] = Real<T>::abs(diag[k]) > Real<T>::tiny ? Real<T>::div(acc, diag[k]) : T(0);
   }
 }
 
@@ -170,17 +178,18 @@ __device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)
   const T b0mag = Real<T>::sqrt(Real<T>::abs(x[0]));
   if (v1) {
     const T sg = neg ? T(-1) : T(1);
+    const T inv0 = sg * Real<T>::rcp(b0mag);
     betas[0] = b0mag;
-    betas[1] = sg * x[1] / b0mag;
-    betas[2] = sg * x[2] / b0mag;
-    betas[3] = sg * x[3] / b0mag;
+    betas[1] = x[1] * inv0;
+    betas[2] = x[2] * inv0;
+    betas[3] = x[3] * inv0;
   } else {
     const bool same_sign = neg ? (x[2] < T(0)) : (x[2] > T(0));
     T b0 = b0mag;
     if (x[1] < T(0)) b0 = -b0;
     betas[0] = b0;
     betas[1] = same_sign ? Real<T>::sqrt(Real<T>::abs(x[2])) : T(0);
-    betas[2] = v3 ? x[3] / b0 : T(0);
+    betas[2] = v3 ? Real<T>::div(x[3], b0) : T(0);
     betas[3] = T(0);
   }
 }

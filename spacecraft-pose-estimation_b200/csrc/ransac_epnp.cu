@@ -292,8 +292,8 @@ __device__ __forceinline__ void control_points5(const float (&pw)[5][3], float (
     float s2 = 0.f;
 #pragma unroll
     for (int k = 0; k < 5; ++k) s2 += Bm[k][i] * Bm[k][i];
-    const float ki = sqrtf(s2 * 0.2f);  // sqrt(lambda_i / 5)
-    inv_k[i] = ki > 1e-12f ? 1.0f / ki : 0.f;
+    const float ki = sqrt_approx(s2 * 0.2f);  // sqrt(lambda_i / 5)
+    inv_k[i] = ki > 1e-12f ? rcp_approx(ki) : 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) cws[i + 1][c] = c0[c] + ki * V[c][i];
   }
@@ -470,9 +470,9 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
       const int si = sub[k];
       const float Xc = R[0][0] * pw[k][0] + R[0][1] * pw[k][1] + R[0][2] * pw[k][2] + t[0];
       const float Yc = R[1][0] * pw[k][0] + R[1][1] * pw[k][1] + R[1][2] * pw[k][2] + t[1];
-      const float iz = 1.0f / (R[2][0] * pw[k][0] + R[2][1] * pw[k][1] + R[2][2] * pw[k][2] + t[2]);
+      const float iz = rcp_approx(R[2][0] * pw[k][0] + R[2][1] * pw[k][1] + R[2][2] * pw[k][2] + t[2]);
       const float du = s_us[si].x - (uc + fu * Xc * iz), dv = s_us[si].y - (vc + fv * Yc * iz);
-      sum += sqrtf(du * du + dv * dv);
+      sum += sqrt_approx(du * du + dv * dv);
     }
     err = sum * 0.2f;
   }
@@ -501,7 +501,7 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
       const float xc = R[0][0] * X + R[0][1] * Y + R[0][2] * Z + t[0];
       const float yc = R[1][0] * X + R[1][1] * Y + R[1][2] * Z + t[1];
       const float zc = R[2][0] * X + R[2][1] * Y + R[2][2] * Z + t[2];
-      const float iz = 1.0f / zc;
+      const float iz = rcp_approx(zc);
       const float x = xc * iz, y = yc * iz;
       const float r2 = x * x + y * y;
       const float cd = 1.0f + ((k3 * r2 + k2) * r2 + k1) * r2;
@@ -533,59 +533,44 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
 constexpr int kT1Threads = 128;
 constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alphas[5][4] (+1: odd stride, conflict-free)
 
-__host__ __device__ constexpr int rr10_p(int r, int k) { return k == 0 ? r : (r + k) % 9; }
-__host__ __device__ constexpr int rr10_q(int r, int k) { return k == 0 ? 9 : (r - k + 9) % 9; }
-
-__device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], int sweeps) {
-  constexpr float kTol2 = 9e-14f;
-#pragma unroll 1
-  for (int sw = 0; sw < sweeps; ++sw) {
+// One Jacobi rotation between the columns at register positions p and q of A, with the two
+// columns SWAPPED on output.  With the swap built in, the odd-even ordering below brings every
+// pair of columns together exactly once per sweep while the pairs always sit at the same register
+// positions, so a sweep is a short loop (no 45-pair unrolled body that overflows the instruction
+// cache, no register moves).
+template <int P, int Q>
+__device__ __forceinline__ void rotate_swap(float (&A)[12][10], float (&d)[10], float g) {
+  constexpr float kTol2 = 9e-14f;  // (3e-7)^2: pairs already orthogonal to FP32 accuracy are only swapped
+  const bool rot = g * g > kTol2 * d[P] * d[Q];
+  float c, s, t;
+  jacobi_angle_fast(d[P], d[Q], rot ? g : 1.0f, c, s, t);
+  c = rot ? c : 1.0f;
+  s = rot ? s : 0.0f;
+  t = rot ? t : 0.0f;
+  const float dp = fmaxf(d[P] - t * g, 0.0f), dq = fmaxf(d[Q] + t * g, 0.0f);
+  d[P] = dq;
+  d[Q] = dp;
 #pragma unroll
-    for (int j = 0; j < 10; ++j) {
-      float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-      for (int r = 0; r < 12; r += 2) s0 = fmaf(A[r][j], A[r][j], s0), s1 = fmaf(A[r + 1][j], A[r + 1][j], s1);
-      d[j] = s0 + s1;
-    }
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      float g[5], c[5], s[5];
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int p = rr10_p(r, k), q = rr10_q(r, k);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-#pragma unroll
-        for (int i = 0; i < 12; i += 3) {
-          s0 = fmaf(A[i][p], A[i][q], s0);
-          s1 = fmaf(A[i + 1][p], A[i + 1][q], s1);
-          s2 = fmaf(A[i + 2][p], A[i + 2][q], s2);
-        }
-        g[k] = s0 + s1 + s2;
-      }
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int p = rr10_p(r, k), q = rr10_q(r, k);
-        const bool rot = g[k] * g[k] > kTol2 * d[p] * d[q];
-        float t;
-        jacobi_angle_fast(d[p], d[q], rot ? g[k] : 1.0f, c[k], s[k], t);
-        c[k] = rot ? c[k] : 1.0f;
-        s[k] = rot ? s[k] : 0.0f;
-        t = rot ? t : 0.0f;
-        d[p] = fmaxf(d[p] - t * g[k], 0.0f);
-        d[q] = fmaxf(d[q] + t * g[k], 0.0f);
-      }
-#pragma unroll
-      for (int k = 0; k < 5; ++k) {
-        const int p = rr10_p(r, k), q = rr10_q(r, k);
-#pragma unroll
-        for (int i = 0; i < 12; ++i) {
-          const float x = A[i][p], y = A[i][q];
-          A[i][p] = c[k] * x - s[k] * y;
-          A[i][q] = s[k] * x + c[k] * y;
-        }
-      }
-    }
+  for (int i = 0; i < 12; ++i) {
+    const float x = A[i][P], y = A[i][Q];
+    A[i][Q] = c * x - s * y;
+    A[i][P] = s * x + c * y;
   }
+}
+
+template <int P, int Q>
+__device__ __forceinline__ float col_dot(const float (&A)[12][10]) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 12; i += 3) {
+    s0 = fmaf(A[i][P], A[i][Q], s0);
+    s1 = fmaf(A[i + 1][P], A[i + 1][Q], s1);
+    s2 = fmaf(A[i + 2][P], A[i + 2][Q], s2);
+  }
+  return s0 + s1 + s2;
+}
+
+__device__ __forceinline__ void col_norms(const float (&A)[12][10], float (&d)[10]) {
 #pragma unroll
   for (int j = 0; j < 10; ++j) {
     float s0 = 0.f, s1 = 0.f;
@@ -593,6 +578,31 @@ __device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], in
     for (int r = 0; r < 12; r += 2) s0 = fmaf(A[r][j], A[r][j], s0), s1 = fmaf(A[r + 1][j], A[r + 1][j], s1);
     d[j] = s0 + s1;
   }
+}
+
+// One-sided Jacobi on the 10 columns of A = M^T in odd-even (transposition) order: a sweep is
+// 5 x { pairs (0,1)(2,3)(4,5)(6,7)(8,9) ; pairs (1,2)(3,4)(5,6)(7,8) } = 45 rotations.
+__device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], int sweeps) {
+#pragma unroll 1
+  for (int it = 0; it < sweeps * 5; ++it) {
+    if (it % 5 == 0) col_norms(A, d);  // exact norms once per sweep; updated by formula in between
+    {
+      const float g0 = col_dot<0, 1>(A), g1 = col_dot<2, 3>(A), g2 = col_dot<4, 5>(A), g3 = col_dot<6, 7>(A), g4 = col_dot<8, 9>(A);
+      rotate_swap<0, 1>(A, d, g0);
+      rotate_swap<2, 3>(A, d, g1);
+      rotate_swap<4, 5>(A, d, g2);
+      rotate_swap<6, 7>(A, d, g3);
+      rotate_swap<8, 9>(A, d, g4);
+    }
+    {
+      const float g0 = col_dot<1, 2>(A), g1 = col_dot<3, 4>(A), g2 = col_dot<5, 6>(A), g3 = col_dot<7, 8>(A);
+      rotate_swap<1, 2>(A, d, g0);
+      rotate_swap<3, 4>(A, d, g1);
+      rotate_swap<5, 6>(A, d, g2);
+      rotate_swap<7, 8>(A, d, g3);
+    }
+  }
+  col_norms(A, d);
 }
 
 __global__ void __launch_bounds__(kT1Threads, 3)
@@ -810,9 +820,9 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblo
       for (int k = 0; k < 5; ++k) {
         const float Xc = R[0][0] * pw[k][0] + R[0][1] * pw[k][1] + R[0][2] * pw[k][2] + t[0];
         const float Yc = R[1][0] * pw[k][0] + R[1][1] * pw[k][1] + R[1][2] * pw[k][2] + t[1];
-        const float iz = 1.0f / (R[2][0] * pw[k][0] + R[2][1] * pw[k][1] + R[2][2] * pw[k][2] + t[2]);
+        const float iz = rcp_approx(R[2][0] * pw[k][0] + R[2][1] * pw[k][1] + R[2][2] * pw[k][2] + t[2]);
         const float du = s_us[si[k]].x - (uc + fu * Xc * iz), dv = s_us[si[k]].y - (vc + fv * Yc * iz);
-        sum += sqrtf(du * du + dv * dv);
+        sum += sqrt_approx(du * du + dv * dv);
       }
       const float err = sum * 0.2f;
       if (variant == 1 || err < eb) {  // N = 1; if (e2 < e1) N = 2; if (e3 < e[N]) N = 3
@@ -839,7 +849,7 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblo
       const float xc = Rb[0][0] * X + Rb[0][1] * Y + Rb[0][2] * Z + tb[0];
       const float yc = Rb[1][0] * X + Rb[1][1] * Y + Rb[1][2] * Z + tb[1];
       const float zc = Rb[2][0] * X + Rb[2][1] * Y + Rb[2][2] * Z + tb[2];
-      const float iz = 1.0f / zc;
+      const float iz = rcp_approx(zc);
       const float x = xc * iz, y = yc * iz;
       const float r2 = x * x + y * y;
       const float cd = 1.0f + ((k3 * r2 + k2) * r2 + k1) * r2;
