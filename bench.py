@@ -61,7 +61,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -303,10 +303,12 @@ def gpu_arm(args, rank, local_rank, world):
                     "d2h_bytes_per_step": B * (28 + 4 + 4 + J * 12), "api": "HeatmapToPose.run_host (pinned host tensors, 512-frame chunks, 2 streams)"},
             "gpu_launches": 4 * args.steps,
             "roofline": {"bound": "hbm", "kernel": "decode_bulk_kernel", "achieved": decode_gbs, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": decode_gbs / hbm_peak, "traffic": 738.29e6 + 4.1e6, "traffic_note": "ncu dram read+write per launch, profiles/decode_r1.md",
+                         "frac": decode_gbs / hbm_peak, "traffic": 738.29e6 + 4.1e6, "traffic_note": "ncu dram read+write per launch, profiles/step_r1.md",
                          "peak_source": peak_src, "ms_per_launch": decode_ms, "algorithmic_bytes_per_launch": B * DECODE_BYTES_PER_FRAME},
             "solver": {"bound": "fp32", "kernel": "hypothesis_kernel (+prep, select/refit)", "achieved": solver_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                        "frac": solver_tflops / fp32_peak, "ms_per_step": solve_ms, "flops_per_hypothesis": HYP_FLOPS,
+                       "flop_model": "SURVEY 8(d) canonical work of the reference algorithm (MtM + 12x12 Jacobi ...), not executed flops: the kernel "
+                                     "reaches the same result with ~3x fewer operations; executed FMA-pipe utilisation is in profiles/step_r1.md",
                        "peak_source": f"148 SMs x 128 FMA/clk x 2 x {sm_mhz:.0f} MHz (nominal pipe width at the observed clock)"},
             "clocks": clocks, "host_call_matches_device_call": same,
         }
@@ -320,7 +322,7 @@ def gpu_arm(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     args = ap.parse_args()

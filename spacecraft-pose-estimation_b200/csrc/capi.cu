@@ -135,6 +135,15 @@ static int hyp_kernel_setting() {
   return variant;
 }
 
+static int refit_fpw_setting() {
+  static int fpw = [] {
+    const char* v = getenv("SPE_REFIT_FPW");  // dev knob
+    const int f = v ? atoi(v) : 32;
+    return f >= 1 && f <= 32 ? f : 32;
+  }();
+  return fpw;
+}
+
 static int jacobi_sweeps_setting() {
   static int sweeps = [] {
     const char* v = getenv("SPE_JACOBI_SWEEPS");  // dev knob
@@ -163,6 +172,7 @@ int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int 
   a.conf_floor = conf_floor;
   a.jacobi_sweeps = jacobi_sweeps_setting();
   a.kernel_variant = hyp_kernel_setting();
+  a.refit_frames_per_warp = refit_fpw_setting();
   a.pose7 = pose7;
   a.inlier_mask = inlier_mask;
   a.status = status;

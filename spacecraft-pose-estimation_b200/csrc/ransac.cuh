@@ -48,6 +48,7 @@ struct RansacArgs {
   double confidence;
   float conf_floor;  // < 0: the reference's adaptive filter
   int jacobi_sweeps;
+  int refit_frames_per_warp;  // 1..32, see select_refit_kernel
   int kernel_variant;  // 0: thread per hypothesis (default), 1: 4 lanes per hypothesis
   float* pose7;           // [B,7]
   uint32_t* inlier_mask;  // [B]

@@ -1212,8 +1212,13 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
   }
 }
 
-__global__ void __launch_bounds__(32) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// The kernel is serial-latency bound: its duration is the time ONE thread needs for its frame
+// (~100 k dependent-ish float64 instructions), whatever the batch size.  `fpw` (frames per warp,
+// dev knob SPE_REFIT_FPW) was swept 32/16/8/4/2 on B200: 2.09/2.09/2.10/2.31/2.82 ms per step,
+// i.e. spreading frames over more warps buys nothing; shortening the chain is the lever.
+__global__ void __launch_bounds__(32) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int fpw) {
+  if ((int)threadIdx.x >= fpw) return;
+  const int b = blockIdx.x * fpw + threadIdx.x;
   if (b >= a.B) return;
   const int n = ws.n[b];
   const unsigned vis = ws.vis[b];
@@ -1305,7 +1310,8 @@ cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const Ransac
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
-  select_refit_kernel<<<(a.B + 31) / 32, 32, 0, stream>>>(dm, a, ws);
+  const int fpw = a.refit_frames_per_warp;
+  select_refit_kernel<<<(a.B + fpw - 1) / fpw, 32, 0, stream>>>(dm, a, ws, fpw);
   return cudaGetLastError();
 }
 
