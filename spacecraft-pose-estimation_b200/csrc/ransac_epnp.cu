@@ -533,28 +533,39 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
 constexpr int kT1Threads = 128;
 constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alphas[5][4] (+1: odd stride, conflict-free)
 
-// One Jacobi rotation between the columns at register positions p and q of A, with the two
+// One Jacobi rotation between the columns at register positions P and Q of A, with the two
 // columns SWAPPED on output.  With the swap built in, the odd-even ordering below brings every
 // pair of columns together exactly once per sweep while the pairs always sit at the same register
 // positions, so a sweep is a short loop (no 45-pair unrolled body that overflows the instruction
 // cache, no register moves).
+//
+// Columns are stored scaled ("fast Givens"): true column j = w[j] * A[:, j].  A rotation then
+// costs two FMAs per row instead of four multiply-adds,
+//     new Q = c wP (x - t wQ/wP y),   new P = c wQ (y + t wP/wQ x),
+// with the factors c wP, c wQ absorbed into w.  d[] holds the TRUE squared norms.
 template <int P, int Q>
-__device__ __forceinline__ void rotate_swap(float (&A)[12][10], float (&d)[10], float g) {
+__device__ __forceinline__ void rotate_swap(float (&A)[12][10], float (&w)[10], float (&d)[10], float g_scaled) {
   constexpr float kTol2 = 9e-14f;  // (3e-7)^2: pairs already orthogonal to FP32 accuracy are only swapped
+  const float wp = w[P], wq = w[Q];
+  const float g = g_scaled * wp * wq;
   const bool rot = g * g > kTol2 * d[P] * d[Q];
-  float c, s, t;
-  jacobi_angle_fast(d[P], d[Q], rot ? g : 1.0f, c, s, t);
-  c = rot ? c : 1.0f;
-  s = rot ? s : 0.0f;
+  // t = tan(theta) = 2g / (h + sign(h) sqrt(h^2 + 4 g^2)), h = dQ - dP; c = rsqrt(1 + t^2): 3 MUFU
+  const float h = d[Q] - d[P], gg = g + g;
+  const float q = sqrt_approx(fmaf(h, h, gg * gg));
+  float t = gg * rcp_approx(h + copysignf(q, h));
   t = rot ? t : 0.0f;
+  const float c = rsqrt_approx(fmaf(t, t, 1.0f));
   const float dp = fmaxf(d[P] - t * g, 0.0f), dq = fmaxf(d[Q] + t * g, 0.0f);
   d[P] = dq;
   d[Q] = dp;
+  const float tau1 = t * wq * rcp_approx(wp), tau2 = t * wp * rcp_approx(wq);
+  w[Q] = c * wp;
+  w[P] = c * wq;
 #pragma unroll
   for (int i = 0; i < 12; ++i) {
     const float x = A[i][P], y = A[i][Q];
-    A[i][Q] = c * x - s * y;
-    A[i][P] = s * x + c * y;
+    A[i][Q] = fmaf(-tau1, y, x);
+    A[i][P] = fmaf(tau2, x, y);
   }
 }
 
@@ -570,12 +581,19 @@ __device__ __forceinline__ float col_dot(const float (&A)[12][10]) {
   return s0 + s1 + s2;
 }
 
-__device__ __forceinline__ void col_norms(const float (&A)[12][10], float (&d)[10]) {
+// fold the scale factors back into the columns and recompute the exact squared norms
+__device__ __forceinline__ void fold_and_norms(float (&A)[12][10], float (&w)[10], float (&d)[10]) {
 #pragma unroll
   for (int j = 0; j < 10; ++j) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int r = 0; r < 12; r += 2) s0 = fmaf(A[r][j], A[r][j], s0), s1 = fmaf(A[r + 1][j], A[r + 1][j], s1);
+    for (int r = 0; r < 12; r += 2) {
+      A[r][j] *= w[j];
+      A[r + 1][j] *= w[j];
+      s0 = fmaf(A[r][j], A[r][j], s0);
+      s1 = fmaf(A[r + 1][j], A[r + 1][j], s1);
+    }
+    w[j] = 1.0f;
     d[j] = s0 + s1;
   }
 }
@@ -583,26 +601,29 @@ __device__ __forceinline__ void col_norms(const float (&A)[12][10], float (&d)[1
 // One-sided Jacobi on the 10 columns of A = M^T in odd-even (transposition) order: a sweep is
 // 5 x { pairs (0,1)(2,3)(4,5)(6,7)(8,9) ; pairs (1,2)(3,4)(5,6)(7,8) } = 45 rotations.
 __device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], int sweeps) {
+  float w[10];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) w[j] = 1.0f;
 #pragma unroll 1
   for (int it = 0; it < sweeps * 5; ++it) {
-    if (it % 5 == 0) col_norms(A, d);  // exact norms once per sweep; updated by formula in between
+    if (it % 5 == 0) fold_and_norms(A, w, d);  // once per sweep; norms follow the update formula in between
     {
       const float g0 = col_dot<0, 1>(A), g1 = col_dot<2, 3>(A), g2 = col_dot<4, 5>(A), g3 = col_dot<6, 7>(A), g4 = col_dot<8, 9>(A);
-      rotate_swap<0, 1>(A, d, g0);
-      rotate_swap<2, 3>(A, d, g1);
-      rotate_swap<4, 5>(A, d, g2);
-      rotate_swap<6, 7>(A, d, g3);
-      rotate_swap<8, 9>(A, d, g4);
+      rotate_swap<0, 1>(A, w, d, g0);
+      rotate_swap<2, 3>(A, w, d, g1);
+      rotate_swap<4, 5>(A, w, d, g2);
+      rotate_swap<6, 7>(A, w, d, g3);
+      rotate_swap<8, 9>(A, w, d, g4);
     }
     {
       const float g0 = col_dot<1, 2>(A), g1 = col_dot<3, 4>(A), g2 = col_dot<5, 6>(A), g3 = col_dot<7, 8>(A);
-      rotate_swap<1, 2>(A, d, g0);
-      rotate_swap<3, 4>(A, d, g1);
-      rotate_swap<5, 6>(A, d, g2);
-      rotate_swap<7, 8>(A, d, g3);
+      rotate_swap<1, 2>(A, w, d, g0);
+      rotate_swap<3, 4>(A, w, d, g1);
+      rotate_swap<5, 6>(A, w, d, g2);
+      rotate_swap<7, 8>(A, w, d, g3);
     }
   }
-  col_norms(A, d);
+  fold_and_norms(A, w, d);
 }
 
 __global__ void __launch_bounds__(kT1Threads, 3)
