@@ -799,7 +799,7 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblo
     for (int variant = 1; variant <= 3; ++variant) {
       float betas[4];
       approx_betas<float>(L, rho, variant, betas);
-      gauss_newton<float>(L, rho, betas);
+      gauss_newton<float, true>(L, rho, betas);
       float ccs[4][3];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
