@@ -213,7 +213,7 @@ __device__ __forceinline__ void build_rho(const T (&cws)[4][3], T (&rho)[6]) {
 
 // The three linearised initialisations of EPnP (App. B.3h), variant = 1, 2 or 3, as one piece
 // of straight-line code so that lanes running different variants do not diverge.
-template <typename T>
+template <typename T, bool kNormalEq = false>
 __device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)[6], int variant, T (&betas)[4]) {
   T A[6][5], b[6], x[5];
   const bool v1 = variant == 1, v3 = variant == 3;
@@ -226,7 +226,8 @@ __device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)
     A[k][4] = v3 ? L[k][4] : T(0);
     b[k] = rho[k];
   }
-  lsq_householder<T, 6, 5>(A, b, x);
+  if constexpr (kNormalEq) lsq_normal<T, 6, 5>(A, b, x);  // masked (all-zero) columns come out as x = 0 in both
+  else lsq_householder<T, 6, 5>(A, b, x);
   const bool neg = x[0] < T(0);
   const T b0mag = Real<T>::sqrt(Real<T>::abs(x[0]));
   if (v1) {

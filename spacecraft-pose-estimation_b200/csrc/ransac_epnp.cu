@@ -545,17 +545,15 @@ constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alp
 // with the factors c wP, c wQ absorbed into w.  d[] holds the TRUE squared norms.
 template <int P, int Q>
 __device__ __forceinline__ void rotate_swap(float (&A)[12][10], float (&w)[10], float (&d)[10], float g_scaled) {
-  constexpr float kTol2 = 9e-14f;  // (3e-7)^2: pairs already orthogonal to FP32 accuracy are only swapped
   const float wp = w[P], wq = w[Q];
   const float g = g_scaled * wp * wq;
-  const bool rot = g * g > kTol2 * d[P] * d[Q];
-  // t = tan(theta) = 2g / (h + sign(h) sqrt(h^2 + 4 g^2)), h = dQ - dP; c = rsqrt(1 + t^2): 3 MUFU
+  // t = tan(theta) = 2g / (h + sign(h) sqrt(h^2 + 4 g^2)), h = dQ - dP; c = rsqrt(1 + t^2): 3 MUFU.
+  // No "already orthogonal" test: a negligible g gives a negligible t (the 1e-30 keeps 0/0 away).
   const float h = d[Q] - d[P], gg = g + g;
-  const float q = sqrt_approx(fmaf(h, h, gg * gg));
-  float t = gg * rcp_approx(h + copysignf(q, h));
-  t = rot ? t : 0.0f;
+  const float q = sqrt_approx(fmaf(h, h, fmaf(gg, gg, 1e-30f)));
+  const float t = gg * rcp_approx(h + copysignf(q, h));
   const float c = rsqrt_approx(fmaf(t, t, 1.0f));
-  const float dp = fmaxf(d[P] - t * g, 0.0f), dq = fmaxf(d[Q] + t * g, 0.0f);
+  const float dp = fmaf(-t, g, d[P]), dq = fmaf(t, g, d[Q]);
   d[P] = dq;
   d[Q] = dp;
   const float tau1 = t * wq * rcp_approx(wp), tau2 = t * wp * rcp_approx(wq);
@@ -579,6 +577,20 @@ __device__ __forceinline__ float col_dot(const float (&A)[12][10]) {
     s2 = fmaf(A[i + 2][P], A[i + 2][Q], s2);
   }
   return s0 + s1 + s2;
+}
+
+// exact TRUE squared norms of the scaled columns (once per sweep; the update formula drifts)
+__device__ __forceinline__ void true_norms(const float (&A)[12][10], const float (&w)[10], float (&d)[10]) {
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int r = 0; r < 12; r += 2) {
+      s0 = fmaf(A[r][j], A[r][j], s0);
+      s1 = fmaf(A[r + 1][j], A[r + 1][j], s1);
+    }
+    d[j] = (s0 + s1) * (w[j] * w[j]);
+  }
 }
 
 // fold the scale factors back into the columns and recompute the exact squared norms
@@ -606,7 +618,9 @@ __device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], in
   for (int j = 0; j < 10; ++j) w[j] = 1.0f;
 #pragma unroll 1
   for (int it = 0; it < sweeps * 5; ++it) {
-    if (it % 5 == 0) fold_and_norms(A, w, d);  // once per sweep; norms follow the update formula in between
+    // once per sweep; in between the norms follow the update formula.  The scale factors only
+    // shrink by c >= 0.707 per rotation (54 rotations per column in 6 sweeps), far from underflow.
+    if (it % 5 == 0) true_norms(A, w, d);
     {
       const float g0 = col_dot<0, 1>(A), g1 = col_dot<2, 3>(A), g2 = col_dot<4, 5>(A), g3 = col_dot<6, 7>(A), g4 = col_dot<8, 9>(A);
       rotate_swap<0, 1>(A, w, d, g0);
@@ -798,7 +812,7 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblo
 #pragma unroll 1
     for (int variant = 1; variant <= 3; ++variant) {
       float betas[4];
-      approx_betas<float>(L, rho, variant, betas);
+      approx_betas<float, true>(L, rho, variant, betas);
       gauss_newton<float, true>(L, rho, betas);
       float ccs[4][3];
 #pragma unroll
