@@ -113,6 +113,19 @@ int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int 
                         uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* The two halves of spe_ransac_epnp_f32, for callers that pipeline batches: the first scores every
+ * hypothesis (frame preparation + FP32 hypothesis kernel, throughput-bound), the second replays
+ * cv2's sequential acceptance and runs the float64 refit (latency-bound: ~0.3 ms whatever B).
+ * Issued on different streams (with an event in between) the second half of batch i overlaps
+ * the first half of batch i+1.  Both must see the same workspace, B and hypotheses. */
+int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
+                         float reproj_err, float conf_floor, void* workspace,
+                         size_t workspace_bytes, void* stream);
+int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses, double confidence,
+                                float* pose7, uint32_t* inlier_mask, int32_t* status,
+                                int32_t* winner_hyp, double* rt, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* Per-hypothesis scores of the most recent spe_ransac_epnp_f32 call on this workspace, for the
  * parity tests: counts [B,hypotheses] int32 and masks [B,hypotheses] uint32 (DEVICE). */
 int spe_ransac_debug_scores(const spe_model_t* model, const void* workspace, int B, int hypotheses,

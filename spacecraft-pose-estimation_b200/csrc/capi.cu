@@ -154,33 +154,60 @@ static int jacobi_sweeps_setting() {
   return sweeps;
 }
 
-int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, double confidence,
-                        float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, void* workspace, size_t workspace_bytes, spe::RansacArgs& a,
+                            spe::RansacWorkspace& ws) {
   if (model == nullptr || B < 0 || hypotheses < 1 || hypotheses > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
-  if (B == 0) return SPE_OK;
-  if (kpts == nullptr || pose7 == nullptr || inlier_mask == nullptr || status == nullptr) return SPE_ERR_INVALID_ARGUMENT;
-  if (!(reproj_err > 0.f)) return SPE_ERR_INVALID_ARGUMENT;
   const size_t need = spe::ransac_workspace_bytes(model->m.J, B, hypotheses);
-  if (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)) return SPE_ERR_WORKSPACE;
-  spe::RansacArgs a{};
-  a.kpts = kpts;
+  if (B > 0 && (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u))) return SPE_ERR_WORKSPACE;
+  a = spe::RansacArgs{};
   a.B = B;
   a.H = hypotheses;
-  a.reproj_err = reproj_err;
-  a.confidence = confidence;
-  a.conf_floor = conf_floor;
   a.jacobi_sweeps = jacobi_sweeps_setting();
   a.kernel_variant = hyp_kernel_setting();
   a.refit_frames_per_warp = refit_fpw_setting();
+  ws = spe::carve_workspace(workspace, model->m.J, B, hypotheses);
+  return SPE_OK;
+}
+
+int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, float conf_floor,
+                         void* workspace, size_t workspace_bytes, void* stream) {
+  spe::RansacArgs a;
+  spe::RansacWorkspace ws;
+  const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, a, ws);
+  if (rc != SPE_OK || B == 0) return rc;
+  if (kpts == nullptr || !(reproj_err > 0.f)) return SPE_ERR_INVALID_ARGUMENT;
+  a.kpts = kpts;
+  a.reproj_err = reproj_err;
+  a.conf_floor = conf_floor;
+  const cudaError_t e = spe::launch_ransac_score(model->m, a, ws, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
+int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses, double confidence, float* pose7, uint32_t* inlier_mask,
+                                int32_t* status, int32_t* winner_hyp, double* rt, void* workspace, size_t workspace_bytes, void* stream) {
+  spe::RansacArgs a;
+  spe::RansacWorkspace ws;
+  const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, a, ws);
+  if (rc != SPE_OK || B == 0) return rc;
+  if (pose7 == nullptr || inlier_mask == nullptr || status == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  a.confidence = confidence;
   a.pose7 = pose7;
   a.inlier_mask = inlier_mask;
   a.status = status;
   a.winner = winner_hyp;
   a.rt = rt;
-  const spe::RansacWorkspace ws = spe::carve_workspace(workspace, model->m.J, B, hypotheses);
-  const cudaError_t e = spe::launch_ransac_epnp(model->m, a, ws, static_cast<cudaStream_t>(stream));
+  const cudaError_t e = spe::launch_ransac_select_refit(model->m, a, ws, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
+int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, double confidence,
+                        float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (B > 0 && (pose7 == nullptr || inlier_mask == nullptr || status == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
+  const int rc = spe_ransac_score_f32(model, kpts, B, hypotheses, reproj_err, conf_floor, workspace, workspace_bytes, stream);
+  if (rc != SPE_OK) return rc;
+  return spe_ransac_select_refit_f32(model, B, hypotheses, confidence, pose7, inlier_mask, status, winner_hyp, rt, workspace, workspace_bytes,
+                                     stream);
 }
 
 int spe_ransac_debug_scores(const spe_model_t* model, const void* workspace, int B, int hypotheses, int32_t* counts, uint32_t* masks,

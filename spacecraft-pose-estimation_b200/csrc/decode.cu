@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kPlainWarps * 32) decode_plain_kernel(const De
 
 int g_num_sms = 0;
 
-template <int kWarps, int kStages, int kChunk, int kBatch = 32>
+template <int kWarps, int kStages, int kChunk, int kBatch = 32, int kCarveoutPct = -1>
 cudaError_t launch_bulk(const DecodeArgs& a, cudaStream_t stream) {
   constexpr size_t smem = BulkLayout<kWarps, kStages, kChunk, kBatch>::total;
   static_assert(smem <= 227 * 1024, "shared memory budget");
@@ -346,6 +346,10 @@ cudaError_t launch_bulk(const DecodeArgs& a, cudaStream_t stream) {
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(decode_bulk_kernel<kWarps, kStages, kChunk, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    if (kCarveoutPct >= 0) {
+      e = cudaFuncSetAttribute(decode_bulk_kernel<kWarps, kStages, kChunk, kBatch>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveoutPct);
+      if (e != cudaSuccess) return e;
+    }
     configured = true;
   }
   const int ctas_needed = (a.n_maps + kWarps - 1) / kWarps;
@@ -377,9 +381,12 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
       case 3: return launch_bulk<12, 2, 2048>(a, stream);  // 192 KB, 12 warps
       case 4: return launch_bulk<6, 2, 4096>(a, stream);   // 192 KB, 6 warps x 2 stages x 16 KB
       case 5: return launch_bulk<7, 2, 4096, 16>(a, stream);  // 224 KB: 7 warps x 2 stages x 16 KB
-      // measured best on B200 (profiles/decode_variants_r1.md): 12 warps, one 16 KB stage each,
-      // 192 KB of bulk copies in flight per SM, 64x64 maps refine from shared memory
-      default: return launch_bulk<12, 1, 4096>(a, stream);
+      case 6: return launch_bulk<12, 1, 4096>(a, stream);  // 192 KB: 12 warps, one 16 KB stage each
+      // measured best on B200 (profiles/decode_variants_r1.md): 7 warps, one 16 KB stage each =
+      // 112 KB of bulk copies in flight per SM; 64x64 maps refine from shared memory.  The 132 KB
+      // carveout (58 %) is the one the pose kernels use too, so an SM never has to drain to switch
+      // its shared-memory/L1 split when the kernels of consecutive batches overlap.
+      default: return launch_bulk<7, 1, 4096, 32, kSmemCarveoutPct>(a, stream);
     }
   }
   const int ctas_needed = (a.n_maps + kPlainWarps - 1) / kPlainWarps;

@@ -5,6 +5,9 @@
 
 namespace spe {
 
+// Shared-memory carveout preferred by every kernel of the stage (percent of 228 KB -> 132 KB).
+constexpr int kSmemCarveoutPct = 58;
+
 struct DecodeArgs {
   const float* hm;      // [n_maps, H, W]
   int n_maps, J, H, W;  // n_maps = B * J

@@ -60,6 +60,9 @@ struct RansacArgs {
 cudaError_t model_upload(Model& m);
 void model_free(Model& m);
 cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream);
+// the two halves of the above: frame prep + hypothesis scoring, then selection + float64 refit
+cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream);
+cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_debug_scores(const RansacWorkspace& ws, int B, int H, int32_t* counts, uint32_t* masks, cudaStream_t stream);
 
 // OpenCV's RANSAC RNG: minimal sets for `count` points, draw order preserved.

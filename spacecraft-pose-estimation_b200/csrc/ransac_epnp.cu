@@ -27,9 +27,11 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/spe_b200.h"
+#include "decode.cuh"
 #include "epnp_math.cuh"
 #include "ransac.cuh"
 
@@ -1251,9 +1253,10 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
 // (~100 k dependent-ish float64 instructions), whatever the batch size.  `fpw` (frames per warp,
 // dev knob SPE_REFIT_FPW) was swept 32/16/8/4/2 on B200: 2.09/2.09/2.10/2.31/2.82 ms per step,
 // i.e. spreading frames over more warps buys nothing; shortening the chain is the lever.
-__global__ void __launch_bounds__(32) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int fpw) {
-  if ((int)threadIdx.x >= fpw) return;
-  const int b = blockIdx.x * fpw + threadIdx.x;
+__global__ void __launch_bounds__(128) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int fpw) {
+  const int lane = threadIdx.x & 31, warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (lane >= fpw) return;
+  const int b = warp * fpw + lane;
   if (b >= a.B) return;
   const int n = ws.n[b];
   const unsigned vis = ws.vis[b];
@@ -1322,7 +1325,7 @@ __global__ void debug_scores_kernel(RansacWorkspace ws, long long total, int32_t
 
 }  // namespace
 
-cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
+cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
   DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam};
   const int wpb = 4;
@@ -1340,14 +1343,42 @@ cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const Ransac
       const int hblocks = (a.H + kT1Threads - 1) / kT1Threads;
       const long long ctas = (long long)a.B * hblocks;
       if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+      static bool carveout_set = false;
+      if (!carveout_set) {  // same shared-memory/L1 split as the decode kernel (decode.cuh)
+        cudaFuncSetAttribute(hypothesis_kernel_t1, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+        carveout_set = true;
+      }
       hypothesis_kernel_t1<<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, hblocks, thr2, a.jacobi_sweeps, ws);
     }
     e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
   }
+  return e;
+}
+
+cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
+  if (a.B == 0) return cudaSuccess;
+  DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam};
   const int fpw = a.refit_frames_per_warp;
-  select_refit_kernel<<<(a.B + fpw - 1) / fpw, 32, 0, stream>>>(dm, a, ws, fpw);
+  static bool carveout_set = false;
+  if (!carveout_set) {
+    // Without this the kernel (no shared memory of its own) flips idle SMs to an all-L1 split and the
+    // next batch's decode CTAs must wait for it to finish: measured 0.12 -> 0.32 ms decode when overlapped.
+    cudaFuncSetAttribute(select_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    carveout_set = true;
+  }
+  static int wpb = [] {
+    const char* v = getenv("SPE_REFIT_WPB");  // dev knob: warps per CTA
+    const int w = v ? atoi(v) : 1;
+    return w >= 1 && w <= 4 ? w : 1;
+  }();
+  const int warps = (a.B + fpw - 1) / fpw;
+  select_refit_kernel<<<(warps + wpb - 1) / wpb, wpb * 32, 0, stream>>>(dm, a, ws, fpw);
   return cudaGetLastError();
+}
+
+cudaError_t launch_ransac_epnp(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
+  const cudaError_t e = launch_ransac_score(m, a, ws, stream);
+  return e != cudaSuccess ? e : launch_ransac_select_refit(m, a, ws, stream);
 }
 
 cudaError_t launch_debug_scores(const RansacWorkspace& ws, int B, int H, int32_t* counts, uint32_t* masks, cudaStream_t stream) {

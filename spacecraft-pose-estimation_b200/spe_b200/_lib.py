@@ -58,6 +58,10 @@ def _declare(L):
         L.spe_ransac_epnp_f32.restype = c_int
         L.spe_ransac_epnp_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_double, c_float, fp, up, ip, ip, dp,
                                           c_void_p, c_size_t, c_void_p]
+        L.spe_ransac_score_f32.restype = c_int
+        L.spe_ransac_score_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]
+        L.spe_ransac_select_refit_f32.restype = c_int
+        L.spe_ransac_select_refit_f32.argtypes = [c_void_p, c_int, c_int, c_double, fp, up, ip, ip, dp, c_void_p, c_size_t, c_void_p]
         L.spe_ransac_debug_scores.restype = c_int
         L.spe_ransac_debug_scores.argtypes = [c_void_p, c_void_p, c_int, c_int, ip, up, c_void_p]
         L.spe_pipeline_workspace_bytes.restype = c_size_t
@@ -70,7 +74,8 @@ def _declare(L):
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",
     "spe_decode_kpts_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
-    "spe_pnp_model_minimal_sets", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_debug_scores",
+    "spe_pnp_model_minimal_sets", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_score_f32",
+    "spe_ransac_select_refit_f32", "spe_ransac_debug_scores",
     "spe_pipeline_workspace_bytes", "spe_heatmap_to_pose_f32",
 )
 

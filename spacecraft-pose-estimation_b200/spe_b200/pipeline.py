@@ -183,3 +183,74 @@ class HeatmapToPose:
                 })
             self._staging_key = key
         return self._bufs
+
+
+class StreamedHeatmapToPose:
+    """Software-pipelined executor for a STREAM of device-resident batches.
+
+    The stage has a throughput-bound front (decode + hypothesis scoring, ~1.5 ms per 4096 frames)
+    and a latency-bound tail (cv2-sequential selection + float64 refit, ~0.3 ms whatever the batch
+    size, occupying about one warp per SM).  Submitting batch i+1's front on the main stream while
+    batch i's tail (and the final all_gather of its poses) runs on a side stream hides the tail:
+    spe_ransac_score_f32 / spe_ransac_select_refit_f32 are the two halves of the C ABI call.
+    Results of a submit() are valid once its `done` event has completed (wait(), or stream order
+    on the side stream).  `depth` batches are in flight, each with its own buffers.
+    """
+
+    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 2, gather_total: int | None = None, want_rt: bool = False):
+        torch = stage._torch
+        self.stage, self.B, self.depth, self.gather_total = stage, int(batch), int(depth), gather_total
+        dev, J, H = stage.device, stage.solver.J, stage.hypotheses
+        self._L = stage._L
+        self.main = torch.cuda.current_stream(dev)
+        self.side = torch.cuda.Stream(dev)
+        self.ws_bytes = int(self._L.spe_ransac_workspace_bytes(stage.solver.handle, self.B, H))
+        self.slots = []
+        for _ in range(self.depth):
+            done = torch.cuda.Event()
+            done.record(self.main)
+            self.slots.append({
+                "out": StageOutput(torch.empty((self.B, 7), dtype=torch.float32, device=dev), torch.empty((self.B,), dtype=torch.int32, device=dev),
+                                   torch.empty((self.B,), dtype=torch.int32, device=dev), torch.empty((self.B, J, 3), dtype=torch.float32, device=dev)),
+                "rt": torch.empty((self.B, 12), dtype=torch.float64, device=dev) if want_rt else None,
+                "ws": torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev),
+                "scored": torch.cuda.Event(), "done": done, "gathered": None,
+            })
+        self._next = 0
+
+    def submit(self, hm, center, scale, decode_events=None):
+        """Enqueue one batch.  Returns the slot dict: slot['out'] (StageOutput), slot['gathered']
+        (the [N_total,7] tensor if gather_total was given), slot['done'] (event)."""
+        torch = self.stage._torch
+        st = self.stage
+        B, J, H, W = hm.shape
+        assert B == self.B and J == st.solver.J and hm.is_contiguous() and hm.dtype == torch.float32
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % self.depth
+        out, ws = slot["out"], slot["ws"]
+        main, side = self.main, self.side
+        main.wait_event(slot["done"])  # the tail that last used this slot's buffers has finished
+        if decode_events is not None:
+            decode_events[0].record(main)
+        _lib.check(self._L.spe_decode_kpts_f32(hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(st.post_process),
+                                               out.kpts.data_ptr(), None, main.cuda_stream), "spe_decode_kpts_f32")
+        if decode_events is not None:
+            decode_events[1].record(main)
+        _lib.check(self._L.spe_ransac_score_f32(st.solver.handle, out.kpts.data_ptr(), B, st.hypotheses, st.reproj_err, st.conf_floor,
+                                                ws.data_ptr(), ws.numel(), main.cuda_stream), "spe_ransac_score_f32")
+        slot["scored"].record(main)
+        side.wait_event(slot["scored"])
+        _lib.check(self._L.spe_ransac_select_refit_f32(st.solver.handle, B, st.hypotheses, st.confidence, out.pose7.data_ptr(),
+                                                       out.inlier_mask.data_ptr(), out.status.data_ptr(), None,
+                                                       slot["rt"].data_ptr() if slot["rt"] is not None else None, ws.data_ptr(), ws.numel(),
+                                                       side.cuda_stream), "spe_ransac_select_refit_f32")
+        if self.gather_total is not None:
+            with torch.cuda.stream(side):
+                slot["gathered"] = all_gather_rows(out.pose7, self.gather_total)
+        slot["done"].record(side)
+        return slot
+
+    def drain(self):
+        """Make the main stream wait for every tail in flight."""
+        for slot in self.slots:
+            self.main.wait_event(slot["done"])

@@ -121,3 +121,37 @@ def test_full_batch_config_c_decode_property():
         ref = hm[lo:lo + 2048].view(2048, J, -1).argmax(2)
         assert torch.equal(idx[lo:lo + 2048].long(), ref)
         assert torch.equal(m[lo:lo + 2048, :, 0], hm[lo:lo + 2048].view(2048, J, -1).amax(2))
+
+
+def test_streamed_executor_matches_single_calls():
+    """The software-pipelined executor (front of batch i+1 overlapping the tail of batch i on a
+    side stream) returns exactly what back-to-back single calls return, slot reuse included."""
+    import torch
+
+    import spe_b200
+    from spe_b200.pipeline import HeatmapToPose, StreamedHeatmapToPose
+
+    model = spe_b200.models.tango()
+    stage = HeatmapToPose(model, hypotheses=128)
+    batches = [spe_b200.synth.device_heatmaps(model, 256, 64, 64, seed=100 + i, device="cuda") for i in range(5)]
+    expect = []
+    for hm, c, s in batches:
+        o = stage(hm, c, s)
+        expect.append((o.pose7.clone(), o.inlier_mask.clone(), o.status.clone(), o.kpts.clone()))
+    pipe = StreamedHeatmapToPose(stage, 256, depth=2, want_rt=True)
+    got = []
+    for hm, c, s in batches:
+        slot = pipe.submit(hm, c, s)
+        slot["done"].synchronize()  # results of a slot are only valid until it is reused
+        o = slot["out"]
+        got.append((o.pose7.clone(), o.inlier_mask.clone(), o.status.clone(), o.kpts.clone()))
+    # and without synchronising in between (the executor must protect its own buffers)
+    last = None
+    for hm, c, s in batches:
+        last = pipe.submit(hm, c, s)
+    pipe.drain()
+    torch.cuda.synchronize()
+    for e, g in zip(expect, got):
+        for a, b in zip(e, g):
+            assert torch.equal(a, b)
+    assert torch.equal(last["out"].pose7, expect[-1][0])
