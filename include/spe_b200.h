@@ -83,6 +83,22 @@ int spe_decode_kpts_f32(const float* hm, int B, int J, int H, int W, const float
                         const float* scale, int post_process, float* kpts, int32_t* argmax,
                         void* stream);
 
+/* Decode of a combination of K heatmap tensors that is never written to memory.
+ * srcs: HOST array of K DEVICE pointers, each [B,J,H,W] float32.
+ *   SPE_COMBINE_MEAN  ((src0 + src1) + ... ) * (1/K)          model ensemble, validate_cv,
+ *                     landmark_regression/lib/core/function.py:525-536 (torch's tensor/scalar on CUDA)
+ *   SPE_COMBINE_FLIP  K = 2: (src0 + shift(flip_back(src1))) * 0.5   flip test, function.py:347-366;
+ *                     flip_back = lib/utils/transforms.py:15-29.  flip_perm: DEVICE int32 [J], the joint
+ *                     whose flipped map lands on joint j (NULL = no matched pairs, as in this dataset);
+ *                     shift_heatmap = config.TEST.SHIFT_HEATMAP.
+ * Output as spe_decode_kpts_f32. */
+#define SPE_COMBINE_MEAN 0
+#define SPE_COMBINE_FLIP 1
+int spe_decode_combined_kpts_f32(const float* const* srcs, int K, int mode, const int32_t* flip_perm,
+                                 int shift_heatmap, int B, int J, int H, int W, const float* center,
+                                 const float* scale, int post_process, float* kpts, int32_t* argmax,
+                                 void* stream);
+
 /* ---- pose ---------------------------------------------------------------------------------
  * landmarks [J,3] float64 HOST (metres; rounded to float32 internally exactly like cv2 does),
  * K[9] row-major float64 HOST, dist[5] = (k1,k2,p1,p2,k3) float64 HOST (NULL = no distortion).

@@ -28,7 +28,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = ["nvcc", *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, *srcs]
+    extra = os.environ.get("SPE_NVCC_EXTRA", "").split()
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", OUT, *srcs]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(res.stderr)

@@ -77,6 +77,36 @@ int spe_decode_kpts_f32(const float* hm, int B, int J, int H, int W, const float
   return run_decode(hm, B, J, H, W, center, scale, post_process, nullptr, nullptr, kpts, argmax, stream);
 }
 
+int spe_decode_combined_kpts_f32(const float* const* srcs, int K, int mode, const int32_t* flip_perm, int shift_heatmap, int B, int J, int H, int W,
+                                 const float* center, const float* scale, int post_process, float* kpts, int32_t* argmax, void* stream) {
+  if (B < 0 || J <= 0 || H <= 0 || W <= 0 || srcs == nullptr || K < 1 || K > spe::kMaxCombine) return SPE_ERR_INVALID_ARGUMENT;
+  if (mode != SPE_COMBINE_MEAN && mode != SPE_COMBINE_FLIP) return SPE_ERR_INVALID_ARGUMENT;
+  if (mode == SPE_COMBINE_FLIP && K != 2) return SPE_ERR_INVALID_ARGUMENT;
+  if ((long long)H * W > 0x7fffffffLL || (long long)B * J > 0x7fffffffLL) return SPE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SPE_OK;
+  if (center == nullptr || scale == nullptr || kpts == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  spe::CombineArgs a{};
+  for (int k = 0; k < K; ++k) {
+    if (srcs[k] == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+    a.src[k] = srcs[k];
+  }
+  a.K = K;
+  a.mode = mode == SPE_COMBINE_MEAN ? spe::kCombineMean : spe::kCombineFlip;
+  a.flip_perm = flip_perm;
+  a.shift_heatmap = shift_heatmap;
+  a.out.n_maps = B * J;
+  a.out.J = J;
+  a.out.H = H;
+  a.out.W = W;
+  a.out.center = center;
+  a.out.scale = scale;
+  a.out.post_process = post_process;
+  a.out.kpts = kpts;
+  a.out.argmax = argmax;
+  const cudaError_t e = spe::launch_decode_combined(a, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
 // ---- pose ----------------------------------------------------------------------------------
 struct spe_model {
   spe::Model m;

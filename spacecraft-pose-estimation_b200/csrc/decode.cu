@@ -336,6 +336,118 @@ __global__ void __launch_bounds__(kPlainWarps * 32) decode_plain_kernel(const De
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// f2: fused pre-combination + decode.  The reference averages heatmap tensors before decoding:
+//   * flip test (lib/core/function.py:347-366): (out + shift(flip_back(out_flipped))) * 0.5, with
+//     flip_back = reverse W + swap matched joints (lib/utils/transforms.py:15-29) and the 1-px
+//     shift of TEST.SHIFT_HEATMAP (columns 1.. take the flipped value to their left);
+//   * model ensemble (validate_cv, function.py:525-536): ((o0 + o1) + ...) / K — on the GPU torch
+//     evaluates tensor / python-scalar as a multiplication by the float32 reciprocal, which is
+//     what is reproduced here so that maxvals stay bit-identical to the reference run.
+// Combining in the decode read saves writing the averaged tensor and reading it back (2 of K+2
+// passes over HBM).  Warp per map, K coalesced 128-bit streams (the flipped stream is read with
+// 32-bit loads: its reversed, shifted window is never 16-byte aligned).
+struct CombineSrc {
+  const float* p[kMaxCombine];
+};
+
+template <int kMode>
+__device__ __forceinline__ float combined_at(const CombineArgs& a, const CombineSrc& s, int idx, float inv_k) {
+  if (kMode == kCombineMean) {
+    float acc = __ldg(s.p[0] + idx);
+    for (int k = 1; k < a.K; ++k) acc = __fadd_rn(acc, __ldg(s.p[k] + idx));
+    return __fmul_rn(acc, inv_k);
+  } else {
+    const int W = a.out.W;
+    const int y = idx / W, x = idx - y * W;
+    const int xs = a.shift_heatmap ? (x == 0 ? W - 1 : W - x) : W - 1 - x;
+    return __fmul_rn(__fadd_rn(__ldg(s.p[0] + idx), __ldg(s.p[1] + y * W + xs)), 0.5f);
+  }
+}
+
+template <int kMode, bool kVec>
+__global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const DecodeArgs& o = a.out;
+  const int hw = o.H * o.W, W = o.W;
+  const int n_warps = gridDim.x * 8;
+  const float inv_k = 1.0f / (float)a.K;
+  for (int map = blockIdx.x * 8 + warp; map < o.n_maps; map += n_warps) {
+    CombineSrc s;
+    if (kMode == kCombineMean) {
+      for (int k = 0; k < a.K; ++k) s.p[k] = a.src[k] + (size_t)map * hw;
+    } else {
+      const int b = map / o.J, j = map - b * o.J;
+      const int jf = a.flip_perm ? a.flip_perm[j] : j;
+      s.p[0] = a.src[0] + (size_t)map * hw;
+      s.p[1] = a.src[1] + ((size_t)b * o.J + jf) * hw;
+    }
+    Best acc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = Best{-INFINITY, kNoIndex};
+    Best b;
+    if (kVec) {
+      const int nvec = hw >> 2;
+#pragma unroll 2
+      for (int v = lane; v < nvec; v += 32) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(s.p[0]) + v);
+        if (kMode == kCombineMean) {
+          for (int k = 1; k < a.K; ++k) {
+            const float4 r = __ldg(reinterpret_cast<const float4*>(s.p[k]) + v);
+            q.x = __fadd_rn(q.x, r.x), q.y = __fadd_rn(q.y, r.y), q.z = __fadd_rn(q.z, r.z), q.w = __fadd_rn(q.w, r.w);
+          }
+          q.x = __fmul_rn(q.x, inv_k), q.y = __fmul_rn(q.y, inv_k), q.z = __fmul_rn(q.z, inv_k), q.w = __fmul_rn(q.w, inv_k);
+        } else {
+          const int e = 4 * v, y = e / W, x = e - y * W;  // W % 4 == 0: the four elements share a row
+          const float* row = s.p[1] + y * W;
+          float f0, f1, f2, f3;
+          if (a.shift_heatmap) {
+            f0 = __ldg(row + (x == 0 ? W - 1 : W - x)), f1 = __ldg(row + W - x - 1), f2 = __ldg(row + W - x - 2), f3 = __ldg(row + W - x - 3);
+          } else {
+            f0 = __ldg(row + W - 1 - x), f1 = __ldg(row + W - 2 - x), f2 = __ldg(row + W - 3 - x), f3 = __ldg(row + W - 4 - x);
+          }
+          q.x = __fmul_rn(__fadd_rn(q.x, f0), 0.5f), q.y = __fmul_rn(__fadd_rn(q.y, f1), 0.5f);
+          q.z = __fmul_rn(__fadd_rn(q.z, f2), 0.5f), q.w = __fmul_rn(__fadd_rn(q.w, f3), 0.5f);
+        }
+        const int ebase = 4 * v;
+        take(acc[0], q.x, ebase);
+        take(acc[1], q.y, ebase);
+        take(acc[2], q.z, ebase);
+        take(acc[3], q.w, ebase);
+      }
+      const bool owns = 4 * lane < hw;
+      b = Best{acc[0].v, acc[0].i == kNoIndex ? 4 * lane : acc[0].i};
+#pragma unroll
+      for (int k = 1; k < 4; ++k) merge(b, acc[k].v, (acc[k].i == kNoIndex ? 4 * lane : acc[k].i) + k);
+      if (!owns) b = Best{-INFINITY, kNoIndex};
+    } else {
+      b = Best{-INFINITY, kNoIndex};
+      for (int e = lane; e < hw; e += 32) take(b, combined_at<kMode>(a, s, e, inv_k), e);
+      if (b.i == kNoIndex && lane < hw) b.i = lane;
+    }
+    b = warp_merge(b);
+    if (b.v != b.v) {  // NaN maximum: first NaN of the COMBINED map
+      int first = 0;
+      for (int base = 0; base < hw; base += 32) {
+        const int e = base + lane;
+        const float v = e < hw ? combined_at<kMode>(a, s, e, inv_k) : 0.f;
+        const unsigned m = __ballot_sync(kFull, v != v);
+        if (m) {
+          first = base + __ffs(m) - 1;
+          break;
+        }
+      }
+      b.i = first;
+    }
+    if (lane == 0) {
+      finish_map(o, map, b.v, b.i, [&](float& l, float& r, float& u, float& d) {
+        l = combined_at<kMode>(a, s, b.i - 1, inv_k), r = combined_at<kMode>(a, s, b.i + 1, inv_k);
+        u = combined_at<kMode>(a, s, b.i - W, inv_k), d = combined_at<kMode>(a, s, b.i + W, inv_k);
+      });
+    }
+  }
+}
+
 int g_num_sms = 0;
 
 template <int kWarps, int kStages, int kChunk, int kBatch = 32, int kCarveoutPct = -1>
@@ -392,6 +504,31 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
   const int ctas_needed = (a.n_maps + kPlainWarps - 1) / kPlainWarps;
   const int cap = g_num_sms * 8;
   decode_plain_kernel<<<ctas_needed < cap ? ctas_needed : cap, kPlainWarps * 32, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_decode_combined(const CombineArgs& a, cudaStream_t stream) {
+  const DecodeArgs& o = a.out;
+  if (o.n_maps == 0) return cudaSuccess;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+  }
+  bool vec = ((long long)o.H * o.W) % 4 == 0 && o.W % 4 == 0;
+  for (int k = 0; k < a.K; ++k) vec = vec && ((reinterpret_cast<uintptr_t>(a.src[k]) & 15u) == 0);
+  const int ctas_needed = (o.n_maps + 7) / 8;
+  const int cap = g_num_sms * 8;  // 8 CTAs x 8 warps per SM: ~64 x K x 2 128-bit loads in flight per SM
+  const int grid = ctas_needed < cap ? ctas_needed : cap;
+  if (a.mode == kCombineMean) {
+    if (vec) decode_combine_kernel<kCombineMean, true><<<grid, 256, 0, stream>>>(a);
+    else decode_combine_kernel<kCombineMean, false><<<grid, 256, 0, stream>>>(a);
+  } else {
+    if (vec) decode_combine_kernel<kCombineFlip, true><<<grid, 256, 0, stream>>>(a);
+    else decode_combine_kernel<kCombineFlip, false><<<grid, 256, 0, stream>>>(a);
+  }
   return cudaGetLastError();
 }
 

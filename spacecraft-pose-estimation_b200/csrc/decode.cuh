@@ -22,4 +22,16 @@ struct DecodeArgs {
 
 cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream);
 
+// decode of a combination of heatmap tensors that is never materialised.
+constexpr int kMaxCombine = 8;
+enum CombineMode { kCombineMean = 0, kCombineFlip = 1 };
+struct CombineArgs {
+  const float* src[kMaxCombine];  // K tensors [n_maps, H, W]
+  int K, mode;
+  const int32_t* flip_perm;  // DEVICE [J]: joint whose flipped map lands on joint j (nullptr = identity)
+  int shift_heatmap;
+  DecodeArgs out;  // hm unused; everything else as for launch_decode
+};
+cudaError_t launch_decode_combined(const CombineArgs& a, cudaStream_t stream);
+
 }  // namespace spe

@@ -532,6 +532,12 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
 // and the 2-D null space (v0, v1) is the orthogonal complement, built from two columns of the
 // projector I - sum v_i v_i^T.  45 pairs x 12 rows per sweep instead of 66 pairs x 22 rows, no
 // shuffles, no work replicated across lanes; the three beta variants run one after the other.
+#ifndef SPE_T1_REGS
+#define SPE_T1_REGS 168
+#endif
+#ifndef SPE_REFIT_REGS
+#define SPE_REFIT_REGS 255
+#endif
 constexpr int kT1Threads = 128;
 constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alphas[5][4] (+1: odd stride, conflict-free)
 
@@ -642,7 +648,7 @@ __device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], in
   fold_and_norms(A, w, d);
 }
 
-__global__ void __launch_bounds__(kT1Threads, 3)
+__global__ void __maxnreg__(SPE_T1_REGS)
 hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblocks, float thr2, int sweeps, RansacWorkspace ws) {
   __shared__ float s_pw[kMaxLandmarks][3];
   __shared__ float2 s_us[kMaxLandmarks];
@@ -1253,7 +1259,7 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
 // (~100 k dependent-ish float64 instructions), whatever the batch size.  `fpw` (frames per warp,
 // dev knob SPE_REFIT_FPW) was swept 32/16/8/4/2 on B200: 2.09/2.09/2.10/2.31/2.82 ms per step,
 // i.e. spreading frames over more warps buys nothing; shortening the chain is the lever.
-__global__ void __launch_bounds__(128) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int fpw) {
+__global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int fpw) {
   const int lane = threadIdx.x & 31, warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (lane >= fpw) return;
   const int b = warp * fpw + lane;

@@ -8,7 +8,7 @@ The arithmetic lives in libspe_b200.so (CUDA, sm_100a) behind include/spe_b200.h
 """
 from . import models, synth  # noqa: F401
 from ._lib import LIB_PATH, SpeError  # noqa: F401
-from .inference import decode_device, get_final_preds, get_max_preds  # noqa: F401
+from .inference import decode_device, get_final_preds, get_final_preds_combined, get_max_preds  # noqa: F401
 from .pnp import PnPSolver, PoseBatch, solvePnPRansac  # noqa: F401
 
-__all__ = ["get_max_preds", "get_final_preds", "decode_device", "PnPSolver", "PoseBatch", "solvePnPRansac", "models", "synth", "SpeError", "LIB_PATH"]
+__all__ = ["get_max_preds", "get_final_preds", "get_final_preds_combined", "decode_device", "PnPSolver", "PoseBatch", "solvePnPRansac", "models", "synth", "SpeError", "LIB_PATH"]

@@ -111,3 +111,59 @@ def get_final_preds(config, batch_heatmaps, center, scale, return_index: bool = 
         out = (preds.cpu().numpy(), maxvals.cpu().numpy())
         return out + (idx.cpu().numpy(),) if return_index else out
     return (preds, maxvals, idx) if return_index else (preds, maxvals)
+
+
+def get_final_preds_combined(config, heatmaps, center, scale, mode: str = "mean", flip_pairs=(), shift_heatmap: bool = False,
+                             return_index: bool = False):
+    """get_final_preds of a COMBINATION of heatmap tensors, computed while decoding — the combined
+    tensor is never written.
+
+    mode="mean": `heatmaps` is the list of K model outputs of the reference's ensemble validation
+        (validate_cv, lib/core/function.py:525-536): decodes ((o0 + o1) + ...) / K.
+    mode="flip": `heatmaps` = [output, output_flipped] where output_flipped is the network output
+        on the mirrored input, exactly what the reference has before `flip_back`
+        (lib/core/function.py:347-366): decodes (output + shift(flip_back(output_flipped))) * 0.5
+        with `flip_pairs` = val_dataset.flip_pairs and shift_heatmap = config.TEST.SHIFT_HEATMAP.
+    Same return conventions as get_final_preds.
+    """
+    import ctypes
+
+    torch = _lib.require_cuda()
+    L = _lib.lib()
+    hms = list(heatmaps)
+    if mode not in ("mean", "flip"):
+        raise ValueError("mode must be 'mean' or 'flip'")
+    if mode == "flip" and len(hms) != 2:
+        raise ValueError("flip mode takes [output, output_flipped]")
+    if not (1 <= len(hms) <= 8):
+        raise ValueError("between 1 and 8 tensors")
+    is_np = _check_heatmaps(hms[0], torch)
+    dev = _device_of(hms[0], torch)
+    dhm = [_to_device(h, torch, dev, "heatmaps") for h in hms]
+    B, J, H, W = dhm[0].shape
+    for h in dhm:
+        if tuple(h.shape) != (B, J, H, W):
+            raise ValueError("all tensors need the same shape")
+    c = _to_device(center, torch, dev, "center").reshape(-1, 2)
+    s = _to_device(scale, torch, dev, "scale").reshape(-1, 2)
+    if c.shape[0] != B or s.shape[0] != B:
+        raise ValueError("center and scale need one row per frame")
+    perm = None
+    if mode == "flip" and len(flip_pairs) > 0:
+        p = np.arange(J, dtype=np.int32)
+        for a, b in flip_pairs:
+            p[a], p[b] = p[b], p[a]
+        perm = torch.from_numpy(p).to(dev)
+    kpts = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, J), dtype=torch.int32, device=dev) if return_index else None
+    ptrs = (ctypes.c_void_p * len(dhm))(*[h.data_ptr() for h in dhm])
+    with torch.cuda.device(dev):
+        _lib.check(L.spe_decode_combined_kpts_f32(ptrs, len(dhm), 0 if mode == "mean" else 1, perm.data_ptr() if perm is not None else None,
+                                                  int(bool(shift_heatmap)), B, J, H, W, c.data_ptr(), s.data_ptr(),
+                                                  int(_post_process_flag(config)), kpts.data_ptr(), idx.data_ptr() if idx is not None else None,
+                                                  torch.cuda.current_stream(dev).cuda_stream), "spe_decode_combined_kpts_f32")
+    preds, maxvals = kpts[..., :2].contiguous(), kpts[..., 2:].contiguous()
+    if is_np:
+        out = (preds.cpu().numpy(), maxvals.cpu().numpy())
+        return out + (idx.cpu().numpy(),) if return_index else out
+    return (preds, maxvals, idx) if return_index else (preds, maxvals)
