@@ -351,11 +351,12 @@ struct CombineSrc {
   const float* p[kMaxCombine];
 };
 
-template <int kMode>
+template <int kMode, int kK>
 __device__ __forceinline__ float combined_at(const CombineArgs& a, const CombineSrc& s, int idx, float inv_k) {
   if (kMode == kCombineMean) {
     float acc = __ldg(s.p[0] + idx);
-    for (int k = 1; k < a.K; ++k) acc = __fadd_rn(acc, __ldg(s.p[k] + idx));
+#pragma unroll
+    for (int k = 1; k < kK; ++k) acc = __fadd_rn(acc, __ldg(s.p[k] + idx));
     return __fmul_rn(acc, inv_k);
   } else {
     const int W = a.out.W;
@@ -365,7 +366,7 @@ __device__ __forceinline__ float combined_at(const CombineArgs& a, const Combine
   }
 }
 
-template <int kMode, bool kVec>
+template <int kMode, bool kVec, int kK>
 __global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const DecodeArgs& o = a.out;
@@ -375,7 +376,8 @@ __global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a
   for (int map = blockIdx.x * 8 + warp; map < o.n_maps; map += n_warps) {
     CombineSrc s;
     if (kMode == kCombineMean) {
-      for (int k = 0; k < a.K; ++k) s.p[k] = a.src[k] + (size_t)map * hw;
+#pragma unroll
+      for (int k = 0; k < kK; ++k) s.p[k] = a.src[k] + (size_t)map * hw;
     } else {
       const int b = map / o.J, j = map - b * o.J;
       const int jf = a.flip_perm ? a.flip_perm[j] : j;
@@ -388,11 +390,12 @@ __global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a
     Best b;
     if (kVec) {
       const int nvec = hw >> 2;
-#pragma unroll 2
+#pragma unroll(kK >= 4 ? 1 : 2)
       for (int v = lane; v < nvec; v += 32) {
         float4 q = __ldg(reinterpret_cast<const float4*>(s.p[0]) + v);
         if (kMode == kCombineMean) {
-          for (int k = 1; k < a.K; ++k) {
+#pragma unroll
+          for (int k = 1; k < kK; ++k) {
             const float4 r = __ldg(reinterpret_cast<const float4*>(s.p[k]) + v);
             q.x = __fadd_rn(q.x, r.x), q.y = __fadd_rn(q.y, r.y), q.z = __fadd_rn(q.z, r.z), q.w = __fadd_rn(q.w, r.w);
           }
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a
       if (!owns) b = Best{-INFINITY, kNoIndex};
     } else {
       b = Best{-INFINITY, kNoIndex};
-      for (int e = lane; e < hw; e += 32) take(b, combined_at<kMode>(a, s, e, inv_k), e);
+      for (int e = lane; e < hw; e += 32) take(b, combined_at<kMode, kK>(a, s, e, inv_k), e);
       if (b.i == kNoIndex && lane < hw) b.i = lane;
     }
     b = warp_merge(b);
@@ -430,7 +433,7 @@ __global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a
       int first = 0;
       for (int base = 0; base < hw; base += 32) {
         const int e = base + lane;
-        const float v = e < hw ? combined_at<kMode>(a, s, e, inv_k) : 0.f;
+        const float v = e < hw ? combined_at<kMode, kK>(a, s, e, inv_k) : 0.f;
         const unsigned m = __ballot_sync(kFull, v != v);
         if (m) {
           first = base + __ffs(m) - 1;
@@ -441,8 +444,8 @@ __global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a
     }
     if (lane == 0) {
       finish_map(o, map, b.v, b.i, [&](float& l, float& r, float& u, float& d) {
-        l = combined_at<kMode>(a, s, b.i - 1, inv_k), r = combined_at<kMode>(a, s, b.i + 1, inv_k);
-        u = combined_at<kMode>(a, s, b.i - W, inv_k), d = combined_at<kMode>(a, s, b.i + W, inv_k);
+        l = combined_at<kMode, kK>(a, s, b.i - 1, inv_k), r = combined_at<kMode, kK>(a, s, b.i + 1, inv_k);
+        u = combined_at<kMode, kK>(a, s, b.i - W, inv_k), d = combined_at<kMode, kK>(a, s, b.i + W, inv_k);
       });
     }
   }
@@ -523,11 +526,17 @@ cudaError_t launch_decode_combined(const CombineArgs& a, cudaStream_t stream) {
   const int cap = g_num_sms * 8;  // 8 CTAs x 8 warps per SM: ~64 x K x 2 128-bit loads in flight per SM
   const int grid = ctas_needed < cap ? ctas_needed : cap;
   if (a.mode == kCombineMean) {
-    if (vec) decode_combine_kernel<kCombineMean, true><<<grid, 256, 0, stream>>>(a);
-    else decode_combine_kernel<kCombineMean, false><<<grid, 256, 0, stream>>>(a);
+    switch (a.K * 2 + (vec ? 1 : 0)) {
+#define SPE_MEAN_CASE(K_)                                                                                  \
+  case K_ * 2 + 1: decode_combine_kernel<kCombineMean, true, K_><<<grid, 256, 0, stream>>>(a); break;     \
+  case K_ * 2: decode_combine_kernel<kCombineMean, false, K_><<<grid, 256, 0, stream>>>(a); break;
+      SPE_MEAN_CASE(1) SPE_MEAN_CASE(2) SPE_MEAN_CASE(3) SPE_MEAN_CASE(4) SPE_MEAN_CASE(5) SPE_MEAN_CASE(6) SPE_MEAN_CASE(7) SPE_MEAN_CASE(8)
+#undef SPE_MEAN_CASE
+      default: return cudaErrorInvalidValue;
+    }
   } else {
-    if (vec) decode_combine_kernel<kCombineFlip, true><<<grid, 256, 0, stream>>>(a);
-    else decode_combine_kernel<kCombineFlip, false><<<grid, 256, 0, stream>>>(a);
+    if (vec) decode_combine_kernel<kCombineFlip, true, 2><<<grid, 256, 0, stream>>>(a);
+    else decode_combine_kernel<kCombineFlip, false, 2><<<grid, 256, 0, stream>>>(a);
   }
   return cudaGetLastError();
 }
