@@ -260,7 +260,7 @@ def gpu_arm(args, rank, local_rank, world):
                    "spe_decode_kpts_f32")
         lat[1].record(stream)
         _lib.check(L.spe_ransac_epnp_f32(stage.solver.handle, kpts.data_ptr(), B, HYPOTHESES, REPROJ, 0.99, -1.0, pose7_single.data_ptr(), mask.data_ptr(),
-                                         status.data_ptr(), None, None, ws.data_ptr(), ws_bytes, stream.cuda_stream), "spe_ransac_epnp_f32")
+                                         status.data_ptr(), None, None, ws.data_ptr(), ws_bytes, 0, stream.cuda_stream), "spe_ransac_epnp_f32")
         lat[2].record(stream)
         torch.cuda.synchronize(dev)
         single.append((lat[0].elapsed_time(lat[1]), lat[1].elapsed_time(lat[2])))

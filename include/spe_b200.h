@@ -123,11 +123,15 @@ size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypothese
  * inlier_mask [B] uint32 over the J landmarks (bit j); status [B] int32 (spe_frame_status)
  * winner_hyp  [B] int32 index of the accepted hypothesis (-1 none); may be NULL
  * rt          [B,12] float64 = row-major R (9) then t (3) of the final refit; may be NULL
+ * flags       0, or SPE_FLAG_REFINE_LM: after the final EPnP, minimise the reprojection error over the
+ *             inliers (the counterpart of cv2.solvePnPRefineLM; NOT part of the reference's call, whose
+ *             SOLVEPNP_EPNP path ends with EPnP on the inliers — off by default everywhere)
  */
+#define SPE_FLAG_REFINE_LM 1
 int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
                         float reproj_err, double confidence, float conf_floor, float* pose7,
                         uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
-                        void* workspace, size_t workspace_bytes, void* stream);
+                        void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 /* The two halves of spe_ransac_epnp_f32, for callers that pipeline batches: the first scores every
  * hypothesis (frame preparation + FP32 hypothesis kernel, throughput-bound), the second replays
@@ -140,7 +144,7 @@ int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int
 int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses, double confidence,
                                 float* pose7, uint32_t* inlier_mask, int32_t* status,
                                 int32_t* winner_hyp, double* rt, void* workspace,
-                                size_t workspace_bytes, void* stream);
+                                size_t workspace_bytes, int flags, void* stream);
 
 /* Per-hypothesis scores of the most recent spe_ransac_epnp_f32 call on this workspace, for the
  * parity tests: counts [B,hypotheses] int32 and masks [B,hypotheses] uint32 (DEVICE). */
@@ -154,7 +158,7 @@ int spe_heatmap_to_pose_f32(const spe_model_t* model, const float* hm, int B, in
                             const float* center, const float* scale, int post_process,
                             int hypotheses, float reproj_err, double confidence, float conf_floor,
                             float* pose7, uint32_t* inlier_mask, int32_t* status, float* kpts_out,
-                            void* workspace, size_t workspace_bytes, void* stream);
+                            void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 #ifdef __cplusplus
 }

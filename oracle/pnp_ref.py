@@ -157,6 +157,15 @@ def pose_from_keypoints(kpts, landmarks, K, dist, iterations=ITERATIONS_COUNT, r
     return ok, np.concatenate([q, tvec]), mask, rvec, tvec
 
 
+def refine_lm_cv2(obj, img, K, dist, rvec, tvec, inliers):
+    """Optional extra: cv2.solvePnPRefineLM on the RANSAC inliers.  The reference's
+    own call has no such step (flags=SOLVEPNP_EPNP ends with EPnP on the inliers)."""
+    o = np.ascontiguousarray(np.asarray(obj, np.float64)[inliers])
+    i = np.ascontiguousarray(np.asarray(img, np.float32)[inliers])
+    r, t = cv2.solvePnPRefineLM(o, i, K, dist, np.asarray(rvec, np.float64).reshape(3, 1).copy(), np.asarray(tvec, np.float64).reshape(3, 1).copy())
+    return r.ravel(), t.ravel()
+
+
 # ----------------------------------------------------------------------------- parity metrics
 def rotation_angle_deg(Ra: np.ndarray, Rb: np.ndarray) -> float:
     """Geodesic angle between two rotations via atan2(|vee|, (tr-1)/2): resolves 1e-7 deg where

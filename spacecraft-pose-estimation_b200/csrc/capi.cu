@@ -214,7 +214,8 @@ int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int
 }
 
 int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses, double confidence, float* pose7, uint32_t* inlier_mask,
-                                int32_t* status, int32_t* winner_hyp, double* rt, void* workspace, size_t workspace_bytes, void* stream) {
+                                int32_t* status, int32_t* winner_hyp, double* rt, void* workspace, size_t workspace_bytes, int flags,
+                                void* stream) {
   spe::RansacArgs a;
   spe::RansacWorkspace ws;
   const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, a, ws);
@@ -226,18 +227,19 @@ int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses,
   a.status = status;
   a.winner = winner_hyp;
   a.rt = rt;
+  a.refine_lm = (flags & SPE_FLAG_REFINE_LM) ? 1 : 0;
   const cudaError_t e = spe::launch_ransac_select_refit(model->m, a, ws, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
 
 int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, double confidence,
                         float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        void* workspace, size_t workspace_bytes, int flags, void* stream) {
   if (B > 0 && (pose7 == nullptr || inlier_mask == nullptr || status == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
   const int rc = spe_ransac_score_f32(model, kpts, B, hypotheses, reproj_err, conf_floor, workspace, workspace_bytes, stream);
   if (rc != SPE_OK) return rc;
   return spe_ransac_select_refit_f32(model, B, hypotheses, confidence, pose7, inlier_mask, status, winner_hyp, rt, workspace, workspace_bytes,
-                                     stream);
+                                     flags, stream);
 }
 
 int spe_ransac_debug_scores(const spe_model_t* model, const void* workspace, int B, int hypotheses, int32_t* counts, uint32_t* masks,
@@ -257,7 +259,7 @@ size_t spe_pipeline_workspace_bytes(const spe_model_t* model, int B, int J, int 
 int spe_heatmap_to_pose_f32(const spe_model_t* model, const float* hm, int B, int J, int H, int W, const float* center,
                             const float* scale, int post_process, int hypotheses, float reproj_err, double confidence,
                             float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, float* kpts_out, void* workspace,
-                            size_t workspace_bytes, void* stream) {
+                            size_t workspace_bytes, int flags, void* stream) {
   if (model == nullptr || J != model->m.J) return SPE_ERR_INVALID_ARGUMENT;
   if (B == 0) return SPE_OK;
   const size_t need = spe_pipeline_workspace_bytes(model, B, J, hypotheses);
@@ -267,7 +269,7 @@ int spe_heatmap_to_pose_f32(const spe_model_t* model, const float* hm, int B, in
   int rc = spe_decode_kpts_f32(hm, B, J, H, W, center, scale, post_process, kpts, nullptr, stream);
   if (rc != SPE_OK) return rc;
   return spe_ransac_epnp_f32(model, kpts, B, hypotheses, reproj_err, confidence, conf_floor, pose7, inlier_mask, status, nullptr, nullptr,
-                             static_cast<unsigned char*>(workspace) + kp, workspace_bytes - kp, stream);
+                             static_cast<unsigned char*>(workspace) + kp, workspace_bytes - kp, flags, stream);
 }
 
 }  // extern "C"

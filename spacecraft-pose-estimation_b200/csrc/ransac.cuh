@@ -31,6 +31,7 @@ struct Model {
 struct RansacWorkspace {
   double2* und;      // [B,J] undistorted normalised coordinates (float64, for the final refit)
   float2* us_hyp;    // [B,J] ideal pixel coordinates as float32 (for the hypotheses)
+  float2* img;       // [B,J] raw (distorted) pixel coordinates, for the optional LM refinement
   int32_t* n;        // [B] number of landmarks that passed the confidence filter
   uint32_t* vis;     // [B] bit j = landmark j takes part
   uint32_t* masks;   // [B,H] inlier mask of every hypothesis over the J landmarks
@@ -48,6 +49,7 @@ struct RansacArgs {
   double confidence;
   float conf_floor;  // < 0: the reference's adaptive filter
   int jacobi_sweeps;
+  int refine_lm;              // SPE_FLAG_REFINE_LM
   int refit_frames_per_warp;  // 1..32, see select_refit_kernel
   int kernel_variant;  // 0: thread per hypothesis (default), 1: 4 lanes per hypothesis
   float* pose7;           // [B,7]

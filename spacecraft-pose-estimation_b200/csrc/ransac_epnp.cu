@@ -99,6 +99,7 @@ RansacWorkspace carve_workspace(void* base, int J, int B, int H) {
   };
   w.und = static_cast<double2*>(take(sizeof(double2) * (size_t)B * J));
   w.us_hyp = static_cast<float2*>(take(sizeof(float2) * (size_t)B * J));
+  w.img = static_cast<float2*>(take(sizeof(float2) * (size_t)B * J));
   w.n = static_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
   w.vis = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B));
   w.masks = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B * H));
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(128) frame_prep_kernel(DevModel m, const float
       y = (y0 - dy) * icd;
     }
     ws.und[(size_t)b * m.J + lane] = make_double2(x, y);
+    ws.img[(size_t)b * m.J + lane] = make_float2(u, v);
     // hypotheses see the float32-rounded normalised point (cv2 keeps the input dtype), mapped to
     // ideal pixels in float64 by EPnP's init_points, then held in float32 by this implementation
     const double xf = (double)(float)x, yf = (double)(float)y;
@@ -1255,6 +1257,139 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
   }
 }
 
+// Optional reprojection-error refinement of (R, t) over the inliers, the counterpart of
+// cv2.solvePnPRefineLM(obj[inl], img[inl], K, dist, rvec, tvec): Levenberg-Marquardt on
+// sum |project(X_i) - x_i|^2 with the 5-coefficient distortion model, float64.  OpenCV's solver
+// stops within 1e-13 deg of the minimiser (20 iterations, eps = FLT_EPSILON), so a converged
+// minimisation matches it; the rotation is updated by left-multiplied so(3) increments.
+// NOT part of the reference's call (its SOLVEPNP_EPNP path has no LM step).
+__device__ void refine_lm_f64(int n, const double (*pw)[3], const double (*img)[2], const Camera& cam, double (&R)[3][3], double (&t)[3]) {
+  auto cost_and_normal = [&](const double (&Rc)[3][3], const double (&tc)[3], double (*JtJ)[6], double* Jtr) {
+    double S = 0.0;
+    if (JtJ) {
+      for (int i = 0; i < 6; ++i) {
+        Jtr[i] = 0.0;
+        for (int j = 0; j < 6; ++j) JtJ[i][j] = 0.0;
+      }
+    }
+    for (int p = 0; p < n; ++p) {
+      const double X = pw[p][0], Y = pw[p][1], Z = pw[p][2];
+      const double rx = Rc[0][0] * X + Rc[0][1] * Y + Rc[0][2] * Z, ry = Rc[1][0] * X + Rc[1][1] * Y + Rc[1][2] * Z,
+                   rz = Rc[2][0] * X + Rc[2][1] * Y + Rc[2][2] * Z;
+      const double xc = rx + tc[0], yc = ry + tc[1], zc = rz + tc[2];
+      const double iz = 1.0 / zc, x = xc * iz, y = yc * iz;
+      const double r2 = x * x + y * y;
+      const double cd = 1.0 + ((cam.k3 * r2 + cam.k2) * r2 + cam.k1) * r2;
+      const double xd = x * cd + 2.0 * cam.p1 * x * y + cam.p2 * (r2 + 2.0 * x * x);
+      const double yd = y * cd + cam.p1 * (r2 + 2.0 * y * y) + 2.0 * cam.p2 * x * y;
+      const double eu = cam.fx * xd + cam.cx - img[p][0], ev = cam.fy * yd + cam.cy - img[p][1];
+      S += eu * eu + ev * ev;
+      if (JtJ) {
+        const double cp = (3.0 * cam.k3 * r2 + 2.0 * cam.k2) * r2 + cam.k1;  // d cd / d r2
+        const double dxdx = cd + 2.0 * x * x * cp + 2.0 * cam.p1 * y + 6.0 * cam.p2 * x;
+        const double dxdy = 2.0 * x * y * cp + 2.0 * cam.p1 * x + 2.0 * cam.p2 * y;
+        const double dydx = dxdy;
+        const double dydy = cd + 2.0 * y * y * cp + 6.0 * cam.p1 * y + 2.0 * cam.p2 * x;
+        // d(x, y) / d Xc
+        const double a00 = iz, a02 = -x * iz, a11 = iz, a12 = -y * iz;
+        // d(u, v) / d Xc  (2 x 3)
+        const double g[2][3] = {{cam.fx * dxdx * a00, cam.fx * dxdy * a11, cam.fx * (dxdx * a02 + dxdy * a12)},
+                                {cam.fy * dydx * a00, cam.fy * dydy * a11, cam.fy * (dydx * a02 + dydy * a12)}};
+        // d Xc / d(omega, t): omega rotates R X, i.e. d Xc = omega x (R X) + dt
+        double Jr[2][6];
+        for (int e = 0; e < 2; ++e) {
+          Jr[e][0] = g[e][2] * ry - g[e][1] * rz;
+          Jr[e][1] = g[e][0] * rz - g[e][2] * rx;
+          Jr[e][2] = g[e][1] * rx - g[e][0] * ry;
+          Jr[e][3] = g[e][0], Jr[e][4] = g[e][1], Jr[e][5] = g[e][2];
+        }
+        for (int i = 0; i < 6; ++i) {
+          Jtr[i] += Jr[0][i] * eu + Jr[1][i] * ev;
+          for (int j = i; j < 6; ++j) JtJ[i][j] += Jr[0][i] * Jr[0][j] + Jr[1][i] * Jr[1][j];
+        }
+      }
+    }
+    return S;
+  };
+  double JtJ[6][6], Jtr[6];
+  double S = cost_and_normal(R, t, JtJ, Jtr);
+  double lambda = 1e-3;
+  for (int iter = 0; iter < 50; ++iter) {
+    // (JtJ + lambda diag) d = -Jtr, Cholesky on the upper triangle
+    double U[6][6], d[6];
+    bool spd = true;
+    for (int i = 0; i < 6 && spd; ++i) {
+      double dg = JtJ[i][i] * (1.0 + lambda);
+      for (int k = 0; k < i; ++k) dg -= U[k][i] * U[k][i];
+      if (!(dg > 0.0)) {
+        spd = false;
+        break;
+      }
+      const double inv = 1.0 / sqrt(dg);
+      U[i][i] = inv;  // stores 1 / U_ii
+      for (int j = i + 1; j < 6; ++j) {
+        double acc = JtJ[i][j];
+        for (int k = 0; k < i; ++k) acc -= U[k][i] * U[k][j];
+        U[i][j] = acc * inv;
+      }
+    }
+    if (!spd) {
+      lambda = fmax(lambda * 10.0, 1e-6);
+      if (lambda > 1e12) break;
+      continue;
+    }
+    for (int i = 0; i < 6; ++i) {
+      double acc = -Jtr[i];
+      for (int k = 0; k < i; ++k) acc -= U[k][i] * d[k];
+      d[i] = acc * U[i][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+      double acc = d[i];
+      for (int j = i + 1; j < 6; ++j) acc -= U[i][j] * d[j];
+      d[i] = acc * U[i][i];
+    }
+    // candidate: R' = exp([w]x) R, t' = t + dt
+    const double wx = d[0], wy = d[1], wz = d[2];
+    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+    double A_, B_;  // sin(th)/th, (1 - cos th)/th^2
+    if (th < 1e-8) {
+      A_ = 1.0 - th2 / 6.0;
+      B_ = 0.5 - th2 / 24.0;
+    } else {
+      A_ = sin(th) / th;
+      B_ = (1.0 - cos(th)) / th2;
+    }
+    const double K1[3][3] = {{0, -wz, wy}, {wz, 0, -wx}, {-wy, wx, 0}};
+    double E[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        double k2 = 0.0;
+        for (int k = 0; k < 3; ++k) k2 += K1[i][k] * K1[k][j];
+        E[i][j] = (i == j ? 1.0 : 0.0) + A_ * K1[i][j] + B_ * k2;
+      }
+    double Rn[3][3], tn[3];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) Rn[i][j] = E[i][0] * R[0][j] + E[i][1] * R[1][j] + E[i][2] * R[2][j];
+      tn[i] = t[i] + d[3 + i];
+    }
+    const double Sn = cost_and_normal(Rn, tn, nullptr, nullptr);
+    double dmax = 0.0;
+    for (int i = 0; i < 6; ++i) dmax = fmax(dmax, fabs(d[i]));
+    if (Sn <= S) {
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) R[i][j] = Rn[i][j];
+        t[i] = tn[i];
+      }
+      lambda = fmax(lambda * 0.1, 1e-12);
+      S = cost_and_normal(R, t, JtJ, Jtr);
+      if (dmax < 1e-12) break;
+    } else {
+      lambda *= 10.0;
+      if (lambda > 1e12 || dmax < 1e-14) break;
+    }
+  }
+}
+
 // The kernel is serial-latency bound: its duration is the time ONE thread needs for its frame
 // (~100 k dependent-ish float64 instructions), whatever the batch size.  `fpw` (frames per warp,
 // dev knob SPE_REFIT_FPW) was swept 32/16/8/4/2 on B200: 2.09/2.09/2.10/2.31/2.82 ms per step,
@@ -1292,11 +1427,13 @@ __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, Rans
   }
   double R[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, t[3] = {0, 0, 0};
   if (status == SPE_FRAME_OK) {
-    double pw[kMaxLandmarks][3], und[kMaxLandmarks][2];
+    double pw[kMaxLandmarks][3], und[kMaxLandmarks][2], img[kMaxLandmarks][2];
     int k = 0;
     for (int j = 0; j < m.J; ++j)
       if ((inl >> j) & 1u) {
         for (int c = 0; c < 3; ++c) pw[k][c] = (double)m.landmarks[3 * j + c];
+        const float2 px = ws.img[(size_t)b * m.J + j];
+        img[k][0] = (double)px.x, img[k][1] = (double)px.y;
         const double2 q = ws.und[(size_t)b * m.J + j];
         // RANSAC's final solve converts the image points to float64 before undistorting; the
         // n == 5 shortcut hands cv2.solvePnP the float32 points, whose undistortion stays float32
@@ -1305,6 +1442,7 @@ __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, Rans
         ++k;
       }
     epnp_f64(k, pw, und, m.cam, R, t);
+    if (a.refine_lm) refine_lm_f64(k, pw, img, m.cam, R, t);
   }
   double q[4] = {1, 0, 0, 0};
   if (status == SPE_FRAME_OK) rotation_to_quat(R, q);

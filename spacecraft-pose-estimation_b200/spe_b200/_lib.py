@@ -60,19 +60,21 @@ def _declare(L):
         L.spe_ransac_workspace_bytes.argtypes = [c_void_p, c_int, c_int]
         L.spe_ransac_epnp_f32.restype = c_int
         L.spe_ransac_epnp_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_double, c_float, fp, up, ip, ip, dp,
-                                          c_void_p, c_size_t, c_void_p]
+                                          c_void_p, c_size_t, c_int, c_void_p]
         L.spe_ransac_score_f32.restype = c_int
         L.spe_ransac_score_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]
         L.spe_ransac_select_refit_f32.restype = c_int
-        L.spe_ransac_select_refit_f32.argtypes = [c_void_p, c_int, c_int, c_double, fp, up, ip, ip, dp, c_void_p, c_size_t, c_void_p]
+        L.spe_ransac_select_refit_f32.argtypes = [c_void_p, c_int, c_int, c_double, fp, up, ip, ip, dp, c_void_p, c_size_t, c_int, c_void_p]
         L.spe_ransac_debug_scores.restype = c_int
         L.spe_ransac_debug_scores.argtypes = [c_void_p, c_void_p, c_int, c_int, ip, up, c_void_p]
         L.spe_pipeline_workspace_bytes.restype = c_size_t
         L.spe_pipeline_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int]
         L.spe_heatmap_to_pose_f32.restype = c_int
         L.spe_heatmap_to_pose_f32.argtypes = [c_void_p, fp, c_int, c_int, c_int, c_int, fp, fp, c_int, c_int, c_float, c_double,
-                                              c_float, fp, up, ip, fp, c_void_p, c_size_t, c_void_p]
+                                              c_float, fp, up, ip, fp, c_void_p, c_size_t, c_int, c_void_p]
 
+
+FLAG_REFINE_LM = 1
 
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",

@@ -62,7 +62,7 @@ class HeatmapToPose:
     """The whole stage for one landmark/camera model on one GPU."""
 
     def __init__(self, model: CameraModel, hypotheses: int = 256, reproj_err: float = 15.0, confidence: float = 0.99,
-                 conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, post_process: bool = True, device=None):
+                 conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, post_process: bool = True, device=None, refine: str | None = None):
         torch = _lib.require_cuda()
         self.model = model
         self.hypotheses = int(hypotheses)
@@ -70,6 +70,9 @@ class HeatmapToPose:
         self.confidence = float(confidence)
         self.conf_floor = float(conf_floor)
         self.post_process = bool(post_process)
+        if refine not in (None, "lm"):
+            raise ValueError("refine must be None or 'lm'")
+        self.flags = _lib.FLAG_REFINE_LM if refine == "lm" else 0
         self.solver = PnPSolver(model.landmarks, model.K, model.dist, max_hypotheses=self.hypotheses, device=device)
         self.device = self.solver.device
         self._L = _lib.lib()
@@ -99,7 +102,7 @@ class HeatmapToPose:
             _lib.check(self._L.spe_heatmap_to_pose_f32(
                 self.solver.handle, hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(self.post_process),
                 self.hypotheses, self.reproj_err, self.confidence, self.conf_floor, out.pose7.data_ptr(), out.inlier_mask.data_ptr(),
-                out.status.data_ptr(), out.kpts.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream(dev).cuda_stream),
+                out.status.data_ptr(), out.kpts.data_ptr(), ws.data_ptr(), ws.numel(), self.flags, torch.cuda.current_stream(dev).cuda_stream),
                 "spe_heatmap_to_pose_f32")
         return out
 
@@ -243,7 +246,7 @@ class StreamedHeatmapToPose:
         _lib.check(self._L.spe_ransac_select_refit_f32(st.solver.handle, B, st.hypotheses, st.confidence, out.pose7.data_ptr(),
                                                        out.inlier_mask.data_ptr(), out.status.data_ptr(), None,
                                                        slot["rt"].data_ptr() if slot["rt"] is not None else None, ws.data_ptr(), ws.numel(),
-                                                       side.cuda_stream), "spe_ransac_select_refit_f32")
+                                                       st.flags, side.cuda_stream), "spe_ransac_select_refit_f32")
         if self.gather_total is not None:
             with torch.cuda.stream(side):
                 slot["gathered"] = all_gather_rows(out.pose7, self.gather_total)

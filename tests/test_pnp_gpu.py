@@ -218,3 +218,39 @@ def test_torch_inputs_stay_on_device_and_are_deterministic():
     assert torch.equal(a.pose7, b.pose7) and torch.equal(a.inlier_mask, b.inlier_mask)
     q = a.pose7[:, :4].double()
     assert torch.allclose(q.norm(dim=1), torch.ones(64, dtype=torch.float64, device="cuda"), atol=1e-6)
+
+
+def test_optional_lm_refinement_matches_cv2_refine_lm():
+    """refine="lm" (not part of the reference's call): the GPU's Levenberg-Marquardt result equals
+    cv2.solvePnPRefineLM run on cv2's own RANSAC inliers, on frames with the same inlier set."""
+    import cv2
+
+    from oracle import pnp_ref
+
+    spe, pnp = _spe()
+    m = spe.models.tango()
+    kpts = _clean_frames(m, 128, seed=33, noise_px=2.0)
+    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=256)
+    plain = s.solve(kpts, hypotheses=256)
+    plain_rt = plain.rt.copy()
+    out = s.solve(kpts, hypotheses=256, refine="lm")
+    np.testing.assert_array_equal(out.inlier_mask, plain.inlier_mask)
+    worst_r = worst_t = 0.0
+    moved = []
+    n_cmp = 0
+    for b in range(kpts.shape[0]):
+        img = kpts[b, :, :2].astype(np.float32)
+        ok, rv, tv, inl = pnp_ref.solve_pnp_ransac_cv2(m.landmarks, img, m.K, m.dist)
+        mask = sum(1 << int(i) for i in inl)
+        if not ok or mask != (int(out.inlier_mask[b]) & 0xFFFFFFFF):
+            continue
+        r2, t2 = pnp_ref.refine_lm_cv2(m.landmarks, img, m.K, m.dist, rv, tv, inl)
+        R = out.rt[b, :9].reshape(3, 3)
+        worst_r = max(worst_r, pnp_ref.rotation_angle_deg(R, cv2.Rodrigues(r2)[0]))
+        worst_t = max(worst_t, float(np.linalg.norm(out.rt[b, 9:] - t2) / np.linalg.norm(t2)))
+        moved.append(pnp_ref.rotation_angle_deg(R, plain_rt[b, :9].reshape(3, 3)))
+        n_cmp += 1
+    assert n_cmp >= 120
+    assert worst_r <= ROT_TOL_DEG and worst_t <= T_TOL_REL, (worst_r, worst_t)
+    assert np.median(moved) > 1e-2  # the refinement really changes the EPnP pose (~0.2 deg)
+    print(f"LM refine: {n_cmp} frames, max rot {worst_r:.2e} deg, max t {worst_t:.2e}; median move vs EPnP {np.median(moved):.3f} deg")
