@@ -984,23 +984,29 @@ __device__ void cv_jacobi_rows(double* A, double* w, int n) {
   }
 }
 
-// Symmetric eigendecomposition by Householder tridiagonalisation + implicit QL (the classic
-// tred2/tql2 pair), n <= 12, float64.  Used for MtM in the final refit: ~4x fewer flops and ~8x
-// fewer sqrt/div than the one-sided Jacobi OpenCV runs there, and eigenvector SIGNS do not matter
-// for MtM (they do for the 3x3 PCA, which keeps cv_jacobi_rows).  On return the columns of V are
-// orthonormal eigenvectors and d their eigenvalues in ASCENDING order.
-__device__ void sym_eig_ql(double* V, double* d, double* e, int n) {
-  // --- tred2
-  for (int j = 0; j < n; ++j) d[j] = V[(n - 1) * n + j];
-  for (int i = n - 1; i > 0; --i) {
+// Eigenvectors of the four SMALLEST eigenvalues of a symmetric N x N matrix (float64), for MtM in
+// the final refit: Householder tridiagonalisation (the classic tred2 reduction, reflectors kept,
+// Q never formed), eigenvalues by implicit QL without vectors (tql1), the four wanted
+// eigenvectors of the tridiagonal matrix by inverse iteration (pivoted tridiagonal LU, three
+// iterations, orthogonalised against the vectors already found) and back-transformation through
+// the stored reflectors.  ~5x fewer instructions than accumulating all 12 eigenvectors through QL,
+// ~20x fewer than the one-sided Jacobi OpenCV runs here; residuals |A v - w v| / |A| ~ 4e-16 on EPnP
+// matrices (tools prototype).  Eigenvector SIGNS are irrelevant for MtM (they matter for the 3x3
+// PCA, which keeps cv_jacobi_rows).  V is destroyed.  out[k] <-> k-th smallest eigenvalue.
+template <int N>
+__device__ void sym_eig_smallest4(double (&V)[N][N], double (&out)[4][N]) {
+  double d[N], e[N], hs[N], diag[N];
+  // --- reduction to tridiagonal form
+  for (int j = 0; j < N; ++j) d[j] = V[N - 1][j];
+  for (int i = N - 1; i > 0; --i) {
     double scale = 0.0, h = 0.0;
     for (int k = 0; k < i; ++k) scale += fabs(d[k]);
     if (scale == 0.0) {
       e[i] = d[i - 1];
       for (int j = 0; j < i; ++j) {
-        d[j] = V[(i - 1) * n + j];
-        V[i * n + j] = 0.0;
-        V[j * n + i] = 0.0;
+        d[j] = V[i - 1][j];
+        V[i][j] = 0.0;
+        V[j][i] = 0.0;
       }
     } else {
       const double inv_scale = 1.0 / scale;
@@ -1017,11 +1023,11 @@ __device__ void sym_eig_ql(double* V, double* d, double* e, int n) {
       for (int j = 0; j < i; ++j) e[j] = 0.0;
       for (int j = 0; j < i; ++j) {
         f = d[j];
-        V[j * n + i] = f;
-        g = e[j] + V[j * n + j] * f;
+        V[j][i] = f;
+        g = e[j] + V[j][j] * f;
         for (int k = j + 1; k <= i - 1; ++k) {
-          g += V[k * n + j] * d[k];
-          e[k] += V[k * n + j] * f;
+          g += V[k][j] * d[k];
+          e[k] += V[k][j] * f;
         }
         e[j] = g;
       }
@@ -1036,105 +1042,159 @@ __device__ void sym_eig_ql(double* V, double* d, double* e, int n) {
       for (int j = 0; j < i; ++j) {
         f = d[j];
         g = e[j];
-        for (int k = j; k <= i - 1; ++k) V[k * n + j] -= (f * e[k] + g * d[k]);
-        d[j] = V[(i - 1) * n + j];
-        V[i * n + j] = 0.0;
+        for (int k = j; k <= i - 1; ++k) V[k][j] -= (f * e[k] + g * d[k]);
+        d[j] = V[i - 1][j];
+        V[i][j] = 0.0;
       }
     }
     d[i] = h;
   }
-  for (int i = 0; i < n - 1; ++i) {
-    V[(n - 1) * n + i] = V[i * n + i];
-    V[i * n + i] = 1.0;
-    const double h = d[i + 1];
-    if (h != 0.0) {
-      const double inv_h = 1.0 / h;
-      for (int k = 0; k <= i; ++k) d[k] = V[k * n + i + 1] * inv_h;
-      for (int j = 0; j <= i; ++j) {
-        double g = 0.0;
-        for (int k = 0; k <= i; ++k) g += V[k * n + i + 1] * V[k * n + j];
-        for (int k = 0; k <= i; ++k) V[k * n + j] -= g * d[k];
-      }
-    }
-    for (int k = 0; k <= i; ++k) V[k * n + i + 1] = 0.0;
+  // reflector m (m >= 1) acts on coordinates 0..m-1: u = V[0..m-1][m], h = hs[m]; T = tridiag(diag, e[1..])
+  double tnorm = 0.0;
+  for (int j = 0; j < N; ++j) {
+    hs[j] = d[j];
+    diag[j] = V[j][j];
+    tnorm = fmax(tnorm, fmax(fabs(diag[j]), j > 0 ? fabs(e[j]) : 0.0));
   }
-  for (int j = 0; j < n; ++j) {
-    d[j] = V[(n - 1) * n + j];
-    V[(n - 1) * n + j] = 0.0;
-  }
-  V[(n - 1) * n + n - 1] = 1.0;
   e[0] = 0.0;
-  // --- tql2
-  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
-  e[n - 1] = 0.0;
-  double f = 0.0, tst1 = 0.0;
   const double eps = 2.220446049250313e-16;
-  for (int l = 0; l < n; ++l) {
-    tst1 = fmax(tst1, fabs(d[l]) + fabs(e[l]));
-    int m = l;
-    while (m < n) {
-      if (fabs(e[m]) <= eps * tst1) break;
-      ++m;
-    }
-    if (m > l) {
-      int iter = 0;
-      do {
-        ++iter;
-        double g = d[l];
-        double p = (d[l + 1] - g) / (2.0 * e[l]);
-        double r = hypot(p, 1.0);
-        if (p < 0) r = -r;
-        d[l] = e[l] / (p + r);
-        d[l + 1] = e[l] * (p + r);
-        const double dl1 = d[l + 1];
-        double h = g - d[l];
-        for (int i = l + 2; i < n; ++i) d[i] -= h;
-        f += h;
-        p = d[m];
-        double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
-        const double el1 = e[l + 1];
-        for (int i = m - 1; i >= l; --i) {
-          c3 = c2;
-          c2 = c;
-          s2 = s;
-          g = c * e[i];
-          h = c * p;
-          r = hypot(p, e[i]);
-          e[i + 1] = s * r;
-          s = e[i] / r;
-          c = p / r;
-          p = c * d[i] - s * g;
-          d[i + 1] = h + s * (c * g + s * d[i]);
-          for (int k = 0; k < n; ++k) {
-            h = V[k * n + i + 1];
-            V[k * n + i + 1] = s * V[k * n + i] + c * h;
-            V[k * n + i] = c * V[k * n + i] - s * h;
-          }
-        }
-        p = -s * s2 * c3 * el1 * e[l] / dl1;
-        e[l] = s * p;
-        d[l] = c * p;
-      } while (fabs(e[l]) > eps * tst1 && iter < 60);
-    }
-    d[l] += f;
-    e[l] = 0.0;
-  }
-  // --- ascending order
-  for (int i = 0; i < n - 1; ++i) {
-    int k = i;
-    double p = d[i];
-    for (int j = i + 1; j < n; ++j)
-      if (d[j] < p) {
-        k = j;
-        p = d[j];
+  // --- eigenvalues: implicit QL on a copy (d2, e2)
+  double d2[N], e2[N];
+  for (int j = 0; j < N; ++j) d2[j] = diag[j];
+  for (int j = 1; j < N; ++j) e2[j - 1] = e[j];
+  e2[N - 1] = 0.0;
+  {
+    double f = 0.0, tst1 = 0.0;
+    for (int l = 0; l < N; ++l) {
+      tst1 = fmax(tst1, fabs(d2[l]) + fabs(e2[l]));
+      int m = l;
+      while (m < N) {
+        if (fabs(e2[m]) <= eps * tst1) break;
+        ++m;
       }
-    if (k != i) {
-      d[k] = d[i];
-      d[i] = p;
-      for (int j = 0; j < n; ++j) {
-        const double t = V[j * n + i];
-        V[j * n + i] = V[j * n + k];
-        V[j * n + k] = t;
+      if (m > l) {
+        int iter = 0;
+        do {
+          ++iter;
+          double g = d2[l];
+          double p = (d2[l + 1] - g) / (2.0 * e2[l]);
+          double r = sqrt(fma(p, p, 1.0));
+          if (p < 0) r = -r;
+          d2[l] = e2[l] / (p + r);
+          d2[l + 1] = e2[l] * (p + r);
+          const double dl1 = d2[l + 1];
+          double h = g - d2[l];
+          for (int i = l + 2; i < N; ++i) d2[i] -= h;
+          f += h;
+          p = d2[m];
+          double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
+          const double el1 = e2[l + 1];
+          for (int i = m - 1; i >= l; --i) {
+            c3 = c2;
+            c2 = c;
+            s2 = s;
+            g = c * e2[i];
+            h = c * p;
+            const double rr = fma(p, p, e2[i] * e2[i]);
+            const double rinv = rr > 0.0 ? rsqrt(rr) : 0.0;
+            r = rr * rinv;
+            e2[i + 1] = s * r;
+            s = e2[i] * rinv;
+            c = p * rinv;
+            p = c * d2[i] - s * g;
+            d2[i + 1] = h + s * (c * g + s * d2[i]);
+          }
+          p = -s * s2 * c3 * el1 * e2[l] / dl1;
+          e2[l] = s * p;
+          d2[l] = c * p;
+        } while (fabs(e2[l]) > eps * tst1 && iter < 60);
+      }
+      d2[l] += f;
+      e2[l] = 0.0;
+    }
+  }
+  // the four smallest, ascending
+  double lam[4];
+  for (int k = 0; k < 4; ++k) {
+    int jm = 0;
+    for (int j = 1; j < N; ++j)
+      if (d2[j] < d2[jm]) jm = j;
+    lam[k] = d2[jm];
+    d2[jm] = 1.7976931348623157e308;
+  }
+  // --- inverse iteration on the tridiagonal matrix + back-transformation
+  double prev = 0.0;
+  for (int k = 0; k < 4; ++k) {
+    double l = lam[k];
+    if (k > 0 && l - prev < 10.0 * eps * tnorm) l = prev + 10.0 * eps * tnorm;  // keep numerically equal eigenvalues apart
+    prev = l;
+    double dd[N], dl[N], du[N], du2[N];
+    bool piv[N];
+    for (int j = 0; j < N; ++j) dd[j] = diag[j] - l;
+    for (int j = 0; j < N - 1; ++j) dl[j] = du[j] = e[j + 1], du2[j] = 0.0, piv[j] = false;
+    for (int i = 0; i < N - 1; ++i) {
+      if (fabs(dd[i]) >= fabs(dl[i])) {
+        if (dd[i] == 0.0) dd[i] = eps * tnorm;
+        const double fact = dl[i] / dd[i];
+        dl[i] = fact;
+        dd[i + 1] -= fact * du[i];
+      } else {
+        const double fact = dd[i] / dl[i];
+        dd[i] = dl[i];
+        dl[i] = fact;
+        const double tmp = du[i];
+        du[i] = dd[i + 1];
+        dd[i + 1] = tmp - fact * dd[i + 1];
+        if (i < N - 2) {
+          du2[i] = du[i + 1];
+          du[i + 1] = -fact * du[i + 1];
+        }
+        piv[i] = true;
+      }
+    }
+    if (dd[N - 1] == 0.0) dd[N - 1] = eps * tnorm;
+    double x[N];
+    {
+      double nn = 0.0;
+      for (int j = 0; j < N; ++j) {
+        x[j] = (double)((j * 7 + k * 3) % 5 - 2) + 0.37 * (k + 1);
+        nn += x[j] * x[j];
+      }
+      const double inv = rsqrt(nn);
+      for (int j = 0; j < N; ++j) x[j] *= inv;
+    }
+    for (int it = 0; it < 3; ++it) {
+      for (int i = 0; i < N - 1; ++i) {
+        if (!piv[i]) {
+          x[i + 1] -= dl[i] * x[i];
+        } else {
+          const double tmp = x[i];
+          x[i] = x[i + 1];
+          x[i + 1] = tmp - dl[i] * x[i];
+        }
+      }
+      x[N - 1] /= dd[N - 1];
+      x[N - 2] = (x[N - 2] - du[N - 2] * x[N - 1]) / dd[N - 2];
+      for (int i = N - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / dd[i];
+      for (int j = 0; j < k; ++j) {  // out[j] temporarily holds the tridiagonal-basis vectors
+        double dot = 0.0;
+        for (int i = 0; i < N; ++i) dot += x[i] * out[j][i];
+        for (int i = 0; i < N; ++i) x[i] -= dot * out[j][i];
+      }
+      double nn = 0.0;
+      for (int i = 0; i < N; ++i) nn += x[i] * x[i];
+      const double inv = nn > 0.0 ? rsqrt(nn) : 0.0;
+      for (int i = 0; i < N; ++i) x[i] *= inv;
+    }
+    for (int i = 0; i < N; ++i) out[k][i] = x[i];
+  }
+  for (int k = 0; k < 4; ++k) {  // v = Q y = H_{N-1} ... H_1 y
+    for (int m = 1; m < N; ++m) {
+      if (hs[m] != 0.0) {
+        double dot = 0.0;
+        for (int i = 0; i < m; ++i) dot += V[i][m] * out[k][i];
+        dot /= hs[m];
+        for (int i = 0; i < m; ++i) out[k][i] -= dot * V[i][m];
       }
     }
   }
@@ -1186,7 +1246,7 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
     al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
   }
   // MtM (12x12), accumulated row pair by row pair
-  double mtm[144] = {}, dw[12];  // symmetric: only needs to be accumulated once
+  double mtm[12][12] = {};
   for (int i = 0; i < n; ++i) {
     double r1[12], r2[12];
     for (int j = 0; j < 4; ++j) {
@@ -1194,14 +1254,11 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
       r2[3 * j] = 0.0, r2[3 * j + 1] = al[i][j] * fv, r2[3 * j + 2] = al[i][j] * (vc - us[i][1]);
     }
     for (int r = 0; r < 12; ++r)
-      for (int c = 0; c < 12; ++c) mtm[12 * r + c] += r1[r] * r1[c] + r2[r] * r2[c];
+      for (int c = 0; c < 12; ++c) mtm[r][c] += r1[r] * r1[c] + r2[r] * r2[c];
   }
   // eigenvectors of MtM for the four smallest eigenvalues: v0 = smallest (OpenCV's ut[11]) ... v3
-  double ew[12];
-  sym_eig_ql(mtm, dw, ew, 12);
   double v[4][12];
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 12; ++j) v[i][j] = mtm[12 * j + i];
+  sym_eig_smallest4<12>(mtm, v);
   double L[6][10], rho[6];
   build_L<double>(v, L);
   build_rho<double>(cws, rho);
