@@ -128,6 +128,11 @@ size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypothese
  *             SOLVEPNP_EPNP path ends with EPnP on the inliers — off by default everywhere)
  */
 #define SPE_FLAG_REFINE_LM 1
+/* SPE_FLAG_ADAPTIVE: score the first 32 minimal sets of every frame, replay cv2's acceptance loop
+ * over them, then score only the hypotheses cv2's (shrinking) iteration budget could still reach.
+ * The result is identical to scoring all `hypotheses` (the selection never reads the skipped
+ * entries); the work is what cv2 itself would do, rounded up to blocks of 32.  Off by default. */
+#define SPE_FLAG_ADAPTIVE 2
 int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
                         float reproj_err, double confidence, float conf_floor, float* pose7,
                         uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
@@ -139,8 +144,8 @@ int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int 
  * Issued on different streams (with an event in between) the second half of batch i overlaps
  * the first half of batch i+1.  Both must see the same workspace, B and hypotheses. */
 int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
-                         float reproj_err, float conf_floor, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         float reproj_err, double confidence, float conf_floor, void* workspace,
+                         size_t workspace_bytes, int flags, void* stream);
 int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses, double confidence,
                                 float* pose7, uint32_t* inlier_mask, int32_t* status,
                                 int32_t* winner_hyp, double* rt, void* workspace,

@@ -199,8 +199,8 @@ static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, voi
   return SPE_OK;
 }
 
-int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, float conf_floor,
-                         void* workspace, size_t workspace_bytes, void* stream) {
+int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, double confidence,
+                         float conf_floor, void* workspace, size_t workspace_bytes, int flags, void* stream) {
   spe::RansacArgs a;
   spe::RansacWorkspace ws;
   const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, a, ws);
@@ -208,7 +208,9 @@ int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int
   if (kpts == nullptr || !(reproj_err > 0.f)) return SPE_ERR_INVALID_ARGUMENT;
   a.kpts = kpts;
   a.reproj_err = reproj_err;
+  a.confidence = confidence;
   a.conf_floor = conf_floor;
+  a.adaptive = (flags & SPE_FLAG_ADAPTIVE) ? 1 : 0;
   const cudaError_t e = spe::launch_ransac_score(model->m, a, ws, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
@@ -236,7 +238,7 @@ int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int 
                         float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
                         void* workspace, size_t workspace_bytes, int flags, void* stream) {
   if (B > 0 && (pose7 == nullptr || inlier_mask == nullptr || status == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
-  const int rc = spe_ransac_score_f32(model, kpts, B, hypotheses, reproj_err, conf_floor, workspace, workspace_bytes, stream);
+  const int rc = spe_ransac_score_f32(model, kpts, B, hypotheses, reproj_err, confidence, conf_floor, workspace, workspace_bytes, flags, stream);
   if (rc != SPE_OK) return rc;
   return spe_ransac_select_refit_f32(model, B, hypotheses, confidence, pose7, inlier_mask, status, winner_hyp, rt, workspace, workspace_bytes,
                                      flags, stream);

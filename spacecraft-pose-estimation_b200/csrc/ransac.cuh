@@ -36,6 +36,8 @@ struct RansacWorkspace {
   uint32_t* vis;     // [B] bit j = landmark j takes part
   uint32_t* masks;   // [B,H] inlier mask of every hypothesis over the J landmarks
   uint8_t* counts;   // [B,H] popcount of the above
+  int32_t* need;     // [B] adaptive mode: hypotheses cv2 could still look at after the first pass
+  int frames;        // B
   size_t bytes;
 };
 
@@ -50,6 +52,7 @@ struct RansacArgs {
   float conf_floor;  // < 0: the reference's adaptive filter
   int jacobi_sweeps;
   int refine_lm;              // SPE_FLAG_REFINE_LM
+  int adaptive;               // SPE_FLAG_ADAPTIVE: score only the hypotheses cv2 could look at
   int refit_frames_per_warp;  // 1..32, see select_refit_kernel
   int kernel_variant;  // 0: thread per hypothesis (default), 1: 4 lanes per hypothesis
   float* pose7;           // [B,7]

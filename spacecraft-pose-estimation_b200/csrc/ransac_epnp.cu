@@ -104,6 +104,8 @@ RansacWorkspace carve_workspace(void* base, int J, int B, int H) {
   w.vis = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B));
   w.masks = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B * H));
   w.counts = static_cast<uint8_t*>(take((size_t)B * H));
+  w.need = static_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
+  w.frames = B;
   w.bytes = off;
   return w;
 }
@@ -541,6 +543,7 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
 #define SPE_REFIT_REGS 255
 #endif
 constexpr int kT1Threads = 128;
+__device__ __forceinline__ int ws_frames(const RansacWorkspace& ws) { return ws.frames; }
 constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alphas[5][4] (+1: odd stride, conflict-free)
 
 // One Jacobi rotation between the columns at register positions P and Q of A, with the two
@@ -651,27 +654,38 @@ __device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], in
 }
 
 __global__ void __maxnreg__(SPE_T1_REGS)
-hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblocks, float thr2, int sweeps, RansacWorkspace ws) {
-  __shared__ float s_pw[kMaxLandmarks][3];
-  __shared__ float2 s_us[kMaxLandmarks];
-  __shared__ float2 s_img[kMaxLandmarks];
+hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_begin, int hblocks, const int32_t* __restrict__ need,
+                     float thr2, int sweeps, RansacWorkspace ws) {
+  // One warp = one work item: 32 consecutive hypotheses [h_begin + 32*hb, +32) of frame b.  Warps of
+  // a CTA are independent (different frames in general), each with its own copy of the frame data.
+  constexpr int kWarps = kT1Threads / 32;
+  __shared__ float s_pw_all[kWarps][kMaxLandmarks][3];
+  __shared__ float2 s_us_all[kWarps][kMaxLandmarks];
+  __shared__ float2 s_img_all[kWarps][kMaxLandmarks];
   __shared__ float s_work[kT1Threads][kT1Stride];
 
-  const int b = blockIdx.x / hblocks, hb = blockIdx.x - b * hblocks;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long item = (long long)blockIdx.x * kWarps + warp;
+  const int b = (int)(item / hblocks), hb = (int)(item - (long long)b * hblocks);
+  if (b >= ws_frames(ws)) return;
   const int n = ws.n[b];
   if (n <= kModelPoints) return;
+  const int h = h_begin + hb * 32 + lane;
+  // adaptive second pass: only hypotheses below the frame's remaining budget are scored
+  const int limit = need ? min(need[b], H) : H;
+  if (h_begin + hb * 32 >= limit) return;
   const unsigned vis = ws.vis[b];
-  const int tid = threadIdx.x;
-  if (tid < n) {
-    const int j = __fns(vis, 0, tid + 1);
-    s_pw[tid][0] = m.landmarks[3 * j], s_pw[tid][1] = m.landmarks[3 * j + 1], s_pw[tid][2] = m.landmarks[3 * j + 2];
-    s_us[tid] = ws.us_hyp[(size_t)b * m.J + j];
+  float(*s_pw)[3] = s_pw_all[warp];
+  float2* s_us = s_us_all[warp];
+  float2* s_img = s_img_all[warp];
+  if (lane < n) {
+    const int j = __fns(vis, 0, lane + 1);
+    s_pw[lane][0] = m.landmarks[3 * j], s_pw[lane][1] = m.landmarks[3 * j + 1], s_pw[lane][2] = m.landmarks[3 * j + 2];
+    s_us[lane] = ws.us_hyp[(size_t)b * m.J + j];
     const float* k = kpts + ((size_t)b * m.J + j) * 3;
-    s_img[tid] = make_float2(k[0], k[1]);
+    s_img[lane] = make_float2(k[0], k[1]);
   }
-  __syncthreads();
-
-  const int h = hb * kT1Threads + tid;
+  __syncwarp();
   if (h >= H) return;
   const uint8_t* sub = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
   int si[5];
@@ -907,6 +921,36 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int hblo
   }
   ws.masks[(size_t)b * H + h] = bits;
   ws.counts[(size_t)b * H + h] = (uint8_t)__popc(bits);
+}
+
+// ------------------------------------------------------------------------------------------
+// 2c. adaptive budget (optional): after the first kFirstPass hypotheses of every frame have been
+// scored, replay cv2's acceptance loop over them.  need[b] = how many hypotheses cv2 could still
+// look at (its shrinking iteration budget, capped at H), or 0 when its loop has already ended.
+// The second pass scores only those; select_refit then reads exactly the entries cv2 would read,
+// so the result is identical to scoring all H.
+constexpr int kFirstPass = 32;
+__device__ int update_num_iters(double p, double ep, int max_iters);
+
+__global__ void __launch_bounds__(128) budget_kernel(RansacWorkspace ws, int B, int H, double confidence, int32_t* need) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int n = ws.n[b];
+  int out = 0;
+  if (n > kModelPoints) {
+    const uint8_t* counts = ws.counts + (size_t)b * H;
+    int niters = H, max_good = 0;
+    const int first = min(kFirstPass, H);
+    for (int h = 0; h < min(niters, first); ++h) {
+      const int g = counts[h];
+      if (g > max(max_good, kModelPoints - 1)) {
+        max_good = g;
+        niters = update_num_iters(confidence, (double)(n - g) / n, niters);
+      }
+    }
+    out = niters > first ? min(niters, H) : 0;
+  }
+  need[b] = out;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1540,16 +1584,32 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
       const long long ctas = (long long)a.B * hblocks;
       if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
       hypothesis_kernel<<<(unsigned)ctas, kHypPerCta * kGroup, 0, stream>>>(dm, a.kpts, a.H, hblocks, thr2, a.jacobi_sweeps, ws);
-    } else {  // one thread per hypothesis
-      const int hblocks = (a.H + kT1Threads - 1) / kT1Threads;
-      const long long ctas = (long long)a.B * hblocks;
-      if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+    } else {  // one thread per hypothesis, one warp per (frame, 32 hypotheses)
       static bool carveout_set = false;
       if (!carveout_set) {  // same shared-memory/L1 split as the decode kernel (decode.cuh)
         cudaFuncSetAttribute(hypothesis_kernel_t1, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
         carveout_set = true;
       }
-      hypothesis_kernel_t1<<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, hblocks, thr2, a.jacobi_sweeps, ws);
+      constexpr int kWarps = kT1Threads / 32;
+      auto launch = [&](int h_begin, int h_count, const int32_t* need) -> cudaError_t {
+        const int hblocks = (h_count + 31) / 32;
+        const long long ctas = ((long long)a.B * hblocks + kWarps - 1) / kWarps;
+        if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
+        if (ctas == 0) return cudaSuccess;
+        hypothesis_kernel_t1<<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
+        return cudaGetLastError();
+      };
+      if (a.adaptive && a.H > kFirstPass) {
+        e = launch(0, kFirstPass, nullptr);
+        if (e != cudaSuccess) return e;
+        budget_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(ws, a.B, a.H, a.confidence, ws.need);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = launch(kFirstPass, a.H - kFirstPass, ws.need);
+      } else {
+        e = launch(0, a.H, nullptr);
+      }
+      if (e != cudaSuccess) return e;
     }
     e = cudaGetLastError();
   }

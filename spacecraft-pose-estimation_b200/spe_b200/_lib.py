@@ -62,7 +62,7 @@ def _declare(L):
         L.spe_ransac_epnp_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_double, c_float, fp, up, ip, ip, dp,
                                           c_void_p, c_size_t, c_int, c_void_p]
         L.spe_ransac_score_f32.restype = c_int
-        L.spe_ransac_score_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_float, c_void_p, c_size_t, c_void_p]
+        L.spe_ransac_score_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_double, c_float, c_void_p, c_size_t, c_int, c_void_p]
         L.spe_ransac_select_refit_f32.restype = c_int
         L.spe_ransac_select_refit_f32.argtypes = [c_void_p, c_int, c_int, c_double, fp, up, ip, ip, dp, c_void_p, c_size_t, c_int, c_void_p]
         L.spe_ransac_debug_scores.restype = c_int
@@ -75,6 +75,7 @@ def _declare(L):
 
 
 FLAG_REFINE_LM = 1
+FLAG_ADAPTIVE = 2
 
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",

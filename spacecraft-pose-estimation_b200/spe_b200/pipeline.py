@@ -62,7 +62,8 @@ class HeatmapToPose:
     """The whole stage for one landmark/camera model on one GPU."""
 
     def __init__(self, model: CameraModel, hypotheses: int = 256, reproj_err: float = 15.0, confidence: float = 0.99,
-                 conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, post_process: bool = True, device=None, refine: str | None = None):
+                 conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, post_process: bool = True, device=None, refine: str | None = None,
+                 adaptive: bool = False):
         torch = _lib.require_cuda()
         self.model = model
         self.hypotheses = int(hypotheses)
@@ -72,7 +73,8 @@ class HeatmapToPose:
         self.post_process = bool(post_process)
         if refine not in (None, "lm"):
             raise ValueError("refine must be None or 'lm'")
-        self.flags = _lib.FLAG_REFINE_LM if refine == "lm" else 0
+        # adaptive=True scores only the hypotheses cv2's shrinking budget could reach (identical results)
+        self.flags = (_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0)
         self.solver = PnPSolver(model.landmarks, model.K, model.dist, max_hypotheses=self.hypotheses, device=device)
         self.device = self.solver.device
         self._L = _lib.lib()
@@ -239,8 +241,8 @@ class StreamedHeatmapToPose:
                                                out.kpts.data_ptr(), None, main.cuda_stream), "spe_decode_kpts_f32")
         if decode_events is not None:
             decode_events[1].record(main)
-        _lib.check(self._L.spe_ransac_score_f32(st.solver.handle, out.kpts.data_ptr(), B, st.hypotheses, st.reproj_err, st.conf_floor,
-                                                ws.data_ptr(), ws.numel(), main.cuda_stream), "spe_ransac_score_f32")
+        _lib.check(self._L.spe_ransac_score_f32(st.solver.handle, out.kpts.data_ptr(), B, st.hypotheses, st.reproj_err, st.confidence,
+                                                st.conf_floor, ws.data_ptr(), ws.numel(), st.flags, main.cuda_stream), "spe_ransac_score_f32")
         slot["scored"].record(main)
         side.wait_event(slot["scored"])
         _lib.check(self._L.spe_ransac_select_refit_f32(st.solver.handle, B, st.hypotheses, st.confidence, out.pose7.data_ptr(),

@@ -103,7 +103,8 @@ class PnPSolver:
 
     # -- the batched solve
     def solve_device(self, kpts, hypotheses: int = 256, reproj_err: float = 15.0, confidence: float = 0.99,
-                     conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, want_rt: bool = True, refine: str | None = None) -> PoseBatch:
+                     conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, want_rt: bool = True, refine: str | None = None,
+                     adaptive: bool = False) -> PoseBatch:
         """kpts [B,J,3] float32 CUDA contiguous -> PoseBatch of CUDA tensors.  Enqueues on torch's
         current stream and does not synchronise.  refine="lm" adds a reprojection-error
         Levenberg-Marquardt step on the inliers (cv2.solvePnPRefineLM's result); the reference does
@@ -129,7 +130,8 @@ class PnPSolver:
             _lib.check(self._L.spe_ransac_epnp_f32(self._handle, kpts.data_ptr(), B, int(hypotheses), float(reproj_err),
                                                    float(confidence), float(conf_floor), pose7.data_ptr(), mask.data_ptr(),
                                                    status.data_ptr(), winner.data_ptr(), rt.data_ptr() if want_rt else None,
-                                                   ws.data_ptr(), ws.numel(), _lib.FLAG_REFINE_LM if refine == "lm" else 0, stream),
+                                                   ws.data_ptr(), ws.numel(),
+                                                   (_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0), stream),
                        "spe_ransac_epnp_f32")
         return PoseBatch(pose7, mask, status, winner, rt)
 

@@ -254,3 +254,26 @@ def test_optional_lm_refinement_matches_cv2_refine_lm():
     assert worst_r <= ROT_TOL_DEG and worst_t <= T_TOL_REL, (worst_r, worst_t)
     assert np.median(moved) > 1e-2  # the refinement really changes the EPnP pose (~0.2 deg)
     print(f"LM refine: {n_cmp} frames, max rot {worst_r:.2e} deg, max t {worst_t:.2e}; median move vs EPnP {np.median(moved):.3f} deg")
+
+
+def test_adaptive_budget_gives_identical_results():
+    """SPE_FLAG_ADAPTIVE scores only the hypotheses cv2's shrinking budget could still reach; poses,
+    inlier masks, status and winners must equal the exhaustive run bit for bit — including frames
+    that need the second pass (many outliers) and frames with no model at all."""
+    from oracle import decode_ref
+
+    spe, pnp = _spe()
+    m = spe.models.tango()
+    fr = spe.synth.make_frames(m, 1024, 64, 64, seed=spe.synth.BASE_SEED + 13, p_outlier=0.25)
+    p, mv = decode_ref.get_final_preds_fast(True, fr.heatmaps, fr.center, fr.scale)
+    kpts = np.concatenate([p, mv], -1).astype(np.float32)
+    rng = np.random.default_rng(1)
+    kpts[:8, :, :2] = rng.uniform(0, 1200, (8, 11, 2))  # junk frames: no model, full budget
+    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=256)
+    full = s.solve(kpts, hypotheses=256)
+    full = [x.copy() for x in (full.pose7, full.inlier_mask, full.status, full.winner, full.rt)]
+    ada = s.solve(kpts, hypotheses=256, adaptive=True)
+    for a, b in zip(full, (ada.pose7, ada.inlier_mask, ada.status, ada.winner, ada.rt)):
+        np.testing.assert_array_equal(a, b)
+    assert (full[3] >= 32).sum() > 0, "the sample should contain frames whose winner lies in the second pass"
+    print(f"adaptive: identical on 1024 frames; winners beyond the first pass: {(full[3] >= 32).sum()}, no-model frames: {(full[2] == 3).sum()}")
