@@ -187,6 +187,12 @@ static int jacobi_sweeps_setting() {
 static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, void* workspace, size_t workspace_bytes, spe::RansacArgs& a,
                             spe::RansacWorkspace& ws) {
   if (model == nullptr || B < 0 || hypotheses < 1 || hypotheses > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
+  if (B > 0) {  // the model's tables live on the device it was created on
+    int dev = -1;
+    const cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    if (dev != model->m.device) return SPE_ERR_INVALID_ARGUMENT;
+  }
   const size_t need = spe::ransac_workspace_bytes(model->m.J, B, hypotheses);
   if (B > 0 && (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u))) return SPE_ERR_WORKSPACE;
   a = spe::RansacArgs{};

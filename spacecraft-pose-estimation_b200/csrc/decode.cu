@@ -24,6 +24,7 @@
 #include <stdlib.h>
 
 #include "decode.cuh"
+#include "device_util.cuh"
 
 namespace spe {
 namespace {
@@ -451,61 +452,59 @@ __global__ void __launch_bounds__(256) decode_combine_kernel(const CombineArgs a
   }
 }
 
-int g_num_sms = 0;
-
 template <int kWarps, int kStages, int kChunk, int kBatch = 32, int kCarveoutPct = -1>
-cudaError_t launch_bulk(const DecodeArgs& a, cudaStream_t stream) {
+cudaError_t launch_bulk(const DecodeArgs& a, int dev, int num_sms, cudaStream_t stream) {
   constexpr size_t smem = BulkLayout<kWarps, kStages, kChunk, kBatch>::total;
   static_assert(smem <= 227 * 1024, "shared memory budget");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(decode_bulk_kernel<kWarps, kStages, kChunk, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (kCarveoutPct >= 0) {
-      e = cudaFuncSetAttribute(decode_bulk_kernel<kWarps, kStages, kChunk, kBatch>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveoutPct);
-      if (e != cudaSuccess) return e;
-    }
-    configured = true;
-  }
+  static PerDeviceOnce once;
+  cudaError_t e = once.run(dev, [] {
+    cudaError_t r = cudaFuncSetAttribute(decode_bulk_kernel<kWarps, kStages, kChunk, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (r == cudaSuccess && kCarveoutPct >= 0)
+      r = cudaFuncSetAttribute(decode_bulk_kernel<kWarps, kStages, kChunk, kBatch>, cudaFuncAttributePreferredSharedMemoryCarveout, kCarveoutPct);
+    return r;
+  });
+  if (e != cudaSuccess) return e;
   const int ctas_needed = (a.n_maps + kWarps - 1) / kWarps;
-  const int grid = ctas_needed < g_num_sms ? ctas_needed : g_num_sms;
+  const int grid = ctas_needed < num_sms ? ctas_needed : num_sms;
   decode_bulk_kernel<kWarps, kStages, kChunk, kBatch><<<grid, kWarps * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-int g_decode_variant = 0;  // dev knob (SPE_DECODE_VARIANT): picks the warps x stages x chunk shape
+// dev knob (SPE_DECODE_VARIANT): picks the warps x stages x chunk shape measured in profiles/decode_variants_r1.md
+static int decode_variant() {
+  static const int variant = [] {
+    const char* v = getenv("SPE_DECODE_VARIANT");
+    return v ? atoi(v) : 0;
+  }();
+  return variant;
+}
 
 cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
   if (a.n_maps == 0) return cudaSuccess;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    if (const char* v = getenv("SPE_DECODE_VARIANT")) g_decode_variant = atoi(v);
-  }
+  int dev = 0, num_sms = 0;
+  const cudaError_t de = current_device(dev, num_sms);
+  if (de != cudaSuccess) return de;
   const long long hw = (long long)a.H * a.W;
   const bool aligned = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.hm) & 15u) == 0);
   if (aligned) {
-    switch (g_decode_variant) {
-      case 1: return launch_bulk<4, 3, 4096>(a, stream);   // 192 KB, 4 warps
-      case 2: return launch_bulk<8, 3, 2048>(a, stream);   // 192 KB, 8 warps, 8 KB stages
-      case 3: return launch_bulk<12, 2, 2048>(a, stream);  // 192 KB, 12 warps
-      case 4: return launch_bulk<6, 2, 4096>(a, stream);   // 192 KB, 6 warps x 2 stages x 16 KB
-      case 5: return launch_bulk<7, 2, 4096, 16>(a, stream);  // 224 KB: 7 warps x 2 stages x 16 KB
-      case 6: return launch_bulk<12, 1, 4096>(a, stream);  // 192 KB: 12 warps, one 16 KB stage each
+    switch (decode_variant()) {
+      case 1: return launch_bulk<4, 3, 4096>(a, dev, num_sms, stream);   // 192 KB, 4 warps
+      case 2: return launch_bulk<8, 3, 2048>(a, dev, num_sms, stream);   // 192 KB, 8 warps, 8 KB stages
+      case 3: return launch_bulk<12, 2, 2048>(a, dev, num_sms, stream);  // 192 KB, 12 warps
+      case 4: return launch_bulk<6, 2, 4096>(a, dev, num_sms, stream);   // 192 KB, 6 warps x 2 stages x 16 KB
+      case 5: return launch_bulk<7, 2, 4096, 16>(a, dev, num_sms, stream);  // 224 KB: 7 warps x 2 stages x 16 KB
+      case 6: return launch_bulk<12, 1, 4096>(a, dev, num_sms, stream);  // 192 KB: 12 warps, one 16 KB stage each
       // measured best on B200 (profiles/decode_variants_r1.md): 7 warps, one 16 KB stage each =
       // 112 KB of bulk copies in flight per SM; 64x64 maps refine from shared memory.  The 132 KB
       // carveout (58 %) is the one the pose kernels use too, so an SM never has to drain to switch
       // its shared-memory/L1 split when the kernels of consecutive batches overlap.
-      default: return launch_bulk<7, 1, 4096, 32, kSmemCarveoutPct>(a, stream);
+      default: return launch_bulk<7, 1, 4096, 32, kSmemCarveoutPct>(a, dev, num_sms, stream);
     }
   }
   const int ctas_needed = (a.n_maps + kPlainWarps - 1) / kPlainWarps;
-  const int cap = g_num_sms * 8;
+  const int cap = num_sms * 8;
   decode_plain_kernel<<<ctas_needed < cap ? ctas_needed : cap, kPlainWarps * 32, 0, stream>>>(a);
   return cudaGetLastError();
 }
@@ -513,17 +512,13 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
 cudaError_t launch_decode_combined(const CombineArgs& a, cudaStream_t stream) {
   const DecodeArgs& o = a.out;
   if (o.n_maps == 0) return cudaSuccess;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-  }
+  int dev = 0, num_sms = 0;
+  const cudaError_t de = current_device(dev, num_sms);
+  if (de != cudaSuccess) return de;
   bool vec = ((long long)o.H * o.W) % 4 == 0 && o.W % 4 == 0;
   for (int k = 0; k < a.K; ++k) vec = vec && ((reinterpret_cast<uintptr_t>(a.src[k]) & 15u) == 0);
   const int ctas_needed = (o.n_maps + 7) / 8;
-  const int cap = g_num_sms * 8;  // 8 CTAs x 8 warps per SM: ~64 x K x 2 128-bit loads in flight per SM
+  const int cap = num_sms * 8;  // 8 CTAs x 8 warps per SM: ~64 x K x 2 128-bit loads in flight per SM
   const int grid = ctas_needed < cap ? ctas_needed : cap;
   if (a.mode == kCombineMean) {
     switch (a.K * 2 + (vec ? 1 : 0)) {

@@ -32,6 +32,7 @@
 
 #include "../../include/spe_b200.h"
 #include "decode.cuh"
+#include "device_util.cuh"
 #include "epnp_math.cuh"
 #include "ransac.cuh"
 
@@ -1585,11 +1586,9 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
       if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
       hypothesis_kernel<<<(unsigned)ctas, kHypPerCta * kGroup, 0, stream>>>(dm, a.kpts, a.H, hblocks, thr2, a.jacobi_sweeps, ws);
     } else {  // one thread per hypothesis, one warp per (frame, 32 hypotheses)
-      static bool carveout_set = false;
-      if (!carveout_set) {  // same shared-memory/L1 split as the decode kernel (decode.cuh)
-        cudaFuncSetAttribute(hypothesis_kernel_t1, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
-        carveout_set = true;
-      }
+      static PerDeviceOnce once;  // same shared-memory/L1 split as the decode kernel (decode.cuh)
+      e = once.run(m.device, [] { return cudaFuncSetAttribute(hypothesis_kernel_t1, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct); });
+      if (e != cudaSuccess) return e;
       constexpr int kWarps = kT1Threads / 32;
       auto launch = [&](int h_begin, int h_count, const int32_t* need) -> cudaError_t {
         const int hblocks = (h_count + 31) / 32;
@@ -1620,13 +1619,12 @@ cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, cons
   if (a.B == 0) return cudaSuccess;
   DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam};
   const int fpw = a.refit_frames_per_warp;
-  static bool carveout_set = false;
-  if (!carveout_set) {
-    // Without this the kernel (no shared memory of its own) flips idle SMs to an all-L1 split and the
-    // next batch's decode CTAs must wait for it to finish: measured 0.12 -> 0.32 ms decode when overlapped.
-    cudaFuncSetAttribute(select_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
-    carveout_set = true;
-  }
+  // Without this the kernel (no shared memory of its own) flips idle SMs to an all-L1 split and the
+  // next batch's decode CTAs must wait for it to finish: measured 0.12 -> 0.32 ms decode when overlapped.
+  static PerDeviceOnce once;
+  const cudaError_t ce =
+      once.run(m.device, [] { return cudaFuncSetAttribute(select_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct); });
+  if (ce != cudaSuccess) return ce;
   static int wpb = [] {
     const char* v = getenv("SPE_REFIT_WPB");  // dev knob: warps per CTA
     const int w = v ? atoi(v) : 1;
