@@ -133,6 +133,10 @@ size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypothese
  * The result is identical to scoring all `hypotheses` (the selection never reads the skipped
  * entries); the work is what cv2 itself would do, rounded up to blocks of 32.  Off by default. */
 #define SPE_FLAG_ADAPTIVE 2
+/* SPE_FLAG_BACKGROUND_TAIL (spe_ransac_select_refit_f32): the caller overlaps this call with the
+ * scoring of the next batch on another stream; the refit then keeps its working matrix in local
+ * instead of shared memory so that it fits next to the hypothesis kernel's CTAs. */
+#define SPE_FLAG_BACKGROUND_TAIL 4
 int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
                         float reproj_err, double confidence, float conf_floor, float* pose7,
                         uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,

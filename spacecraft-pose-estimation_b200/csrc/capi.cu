@@ -165,15 +165,6 @@ static int hyp_kernel_setting() {
   return variant;
 }
 
-static int refit_fpw_setting() {
-  static int fpw = [] {
-    const char* v = getenv("SPE_REFIT_FPW");  // dev knob
-    const int f = v ? atoi(v) : 32;
-    return f >= 1 && f <= 32 ? f : 32;
-  }();
-  return fpw;
-}
-
 static int jacobi_sweeps_setting() {
   static int sweeps = [] {
     const char* v = getenv("SPE_JACOBI_SWEEPS");  // dev knob
@@ -200,7 +191,6 @@ static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, voi
   a.H = hypotheses;
   a.jacobi_sweeps = jacobi_sweeps_setting();
   a.kernel_variant = hyp_kernel_setting();
-  a.refit_frames_per_warp = refit_fpw_setting();
   ws = spe::carve_workspace(workspace, model->m.J, B, hypotheses);
   return SPE_OK;
 }
@@ -236,6 +226,7 @@ int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses,
   a.winner = winner_hyp;
   a.rt = rt;
   a.refine_lm = (flags & SPE_FLAG_REFINE_LM) ? 1 : 0;
+  a.refit_background = (flags & SPE_FLAG_BACKGROUND_TAIL) ? 1 : 0;
   const cudaError_t e = spe::launch_ransac_select_refit(model->m, a, ws, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }

@@ -53,7 +53,7 @@ struct RansacArgs {
   int jacobi_sweeps;
   int refine_lm;              // SPE_FLAG_REFINE_LM
   int adaptive;               // SPE_FLAG_ADAPTIVE: score only the hypotheses cv2 could look at
-  int refit_frames_per_warp;  // 1..32, see select_refit_kernel
+  int refit_background;       // the tail runs under other kernels: keep its shared-memory footprint at zero
   int kernel_variant;  // 0: thread per hypothesis (default), 1: 4 lanes per hypothesis
   float* pose7;           // [B,7]
   uint32_t* inlier_mask;  // [B]

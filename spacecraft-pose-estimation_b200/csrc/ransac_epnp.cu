@@ -1038,20 +1038,40 @@ __device__ void cv_jacobi_rows(double* A, double* w, int n) {
 // ~20x fewer than the one-sided Jacobi OpenCV runs here; residuals |A v - w v| / |A| ~ 4e-16 on EPnP
 // matrices (tools prototype).  Eigenvector SIGNS are irrelevant for MtM (they matter for the 3x3
 // PCA, which keeps cv_jacobi_rows).  V is destroyed.  out[k] <-> k-th smallest eigenvalue.
-template <int N>
-__device__ void sym_eig_smallest4(double (&V)[N][N], double (&out)[4][N]) {
+// A per-thread 12x12 float64 matrix kept in SHARED memory, element-major so that the 32 threads of
+// a warp touch 32 consecutive doubles: the refit kernel's working set per thread (~6 KB of local
+// arrays) does not fit the L1 next to the 132 KB shared-memory carveout, and the tridiagonalisation
+// sweeps this matrix many times (long_scoreboard was its top stall with the matrix in local memory).
+struct SmemMat12 {
+  double* base;  // &storage[0][thread]
+  int stride;    // threads per CTA
+  __device__ __forceinline__ double& operator()(int r, int c) const { return base[(r * 12 + c) * stride]; }
+};
+
+struct LocalMat12 {  // the same matrix in the thread's local memory (small footprint, see select_refit_kernel)
+  double (*a)[12];
+  __device__ __forceinline__ double& operator()(int r, int c) const { return a[r][c]; }
+};
+
+// Called by the 4 lanes of a frame's group with identical inputs (sub = lane within the group,
+// gmask = the group's lanes): the reduction and the eigenvalues are computed redundantly, then lane
+// k runs the inverse iteration and the back-transformation of eigenvector k; the iterates are
+// exchanged with shuffles after every iteration and orthonormalised in order by every lane.
+template <int N, typename Mat>
+__device__ void sym_eig_smallest4(Mat V, double (&out)[4][N], int sub, unsigned gmask) {
+  const int gbase = (threadIdx.x & 31) & ~3;
   double d[N], e[N], hs[N], diag[N];
   // --- reduction to tridiagonal form
-  for (int j = 0; j < N; ++j) d[j] = V[N - 1][j];
+  for (int j = 0; j < N; ++j) d[j] = V(N - 1, j);
   for (int i = N - 1; i > 0; --i) {
     double scale = 0.0, h = 0.0;
     for (int k = 0; k < i; ++k) scale += fabs(d[k]);
     if (scale == 0.0) {
       e[i] = d[i - 1];
       for (int j = 0; j < i; ++j) {
-        d[j] = V[i - 1][j];
-        V[i][j] = 0.0;
-        V[j][i] = 0.0;
+        d[j] = V(i - 1, j);
+        V(i, j) = 0.0;
+        V(j, i) = 0.0;
       }
     } else {
       const double inv_scale = 1.0 / scale;
@@ -1068,11 +1088,11 @@ __device__ void sym_eig_smallest4(double (&V)[N][N], double (&out)[4][N]) {
       for (int j = 0; j < i; ++j) e[j] = 0.0;
       for (int j = 0; j < i; ++j) {
         f = d[j];
-        V[j][i] = f;
-        g = e[j] + V[j][j] * f;
+        V(j, i) = f;
+        g = e[j] + V(j, j) * f;
         for (int k = j + 1; k <= i - 1; ++k) {
-          g += V[k][j] * d[k];
-          e[k] += V[k][j] * f;
+          g += V(k, j) * d[k];
+          e[k] += V(k, j) * f;
         }
         e[j] = g;
       }
@@ -1087,18 +1107,18 @@ __device__ void sym_eig_smallest4(double (&V)[N][N], double (&out)[4][N]) {
       for (int j = 0; j < i; ++j) {
         f = d[j];
         g = e[j];
-        for (int k = j; k <= i - 1; ++k) V[k][j] -= (f * e[k] + g * d[k]);
-        d[j] = V[i - 1][j];
-        V[i][j] = 0.0;
+        for (int k = j; k <= i - 1; ++k) V(k, j) -= (f * e[k] + g * d[k]);
+        d[j] = V(i - 1, j);
+        V(i, j) = 0.0;
       }
     }
     d[i] = h;
   }
-  // reflector m (m >= 1) acts on coordinates 0..m-1: u = V[0..m-1][m], h = hs[m]; T = tridiag(diag, e[1..])
+  // reflector m (m >= 1) acts on coordinates 0..m-1: u = V(0..m-1, m), h = hs[m]; T = tridiag(diag, e[1..])
   double tnorm = 0.0;
   for (int j = 0; j < N; ++j) {
     hs[j] = d[j];
-    diag[j] = V[j][j];
+    diag[j] = V(j, j);
     tnorm = fmax(tnorm, fmax(fabs(diag[j]), j > 0 ? fabs(e[j]) : 0.0));
   }
   e[0] = 0.0;
@@ -1167,82 +1187,100 @@ __device__ void sym_eig_smallest4(double (&V)[N][N], double (&out)[4][N]) {
     lam[k] = d2[jm];
     d2[jm] = 1.7976931348623157e308;
   }
-  // --- inverse iteration on the tridiagonal matrix + back-transformation
-  double prev = 0.0;
-  for (int k = 0; k < 4; ++k) {
-    double l = lam[k];
-    if (k > 0 && l - prev < 10.0 * eps * tnorm) l = prev + 10.0 * eps * tnorm;  // keep numerically equal eigenvalues apart
-    prev = l;
-    double dd[N], dl[N], du[N], du2[N];
-    bool piv[N];
-    for (int j = 0; j < N; ++j) dd[j] = diag[j] - l;
-    for (int j = 0; j < N - 1; ++j) dl[j] = du[j] = e[j + 1], du2[j] = 0.0, piv[j] = false;
+  // --- inverse iteration on the tridiagonal matrix (lane k <-> eigenvector k) + back-transformation
+  double l = lam[0];
+  {
+    double prev = 0.0;
+    for (int k = 0; k < 4; ++k) {
+      double lk = lam[k];
+      if (k > 0 && lk - prev < 10.0 * eps * tnorm) lk = prev + 10.0 * eps * tnorm;  // keep numerically equal eigenvalues apart
+      prev = lk;
+      if (k == sub) l = lk;
+    }
+  }
+  double dd[N], dl[N], du[N], du2[N];
+  bool piv[N];
+  for (int j = 0; j < N; ++j) dd[j] = diag[j] - l;
+  for (int j = 0; j < N - 1; ++j) dl[j] = du[j] = e[j + 1], du2[j] = 0.0, piv[j] = false;
+  for (int i = 0; i < N - 1; ++i) {  // pivoted LU of the shifted tridiagonal matrix
+    if (fabs(dd[i]) >= fabs(dl[i])) {
+      if (dd[i] == 0.0) dd[i] = eps * tnorm;
+      const double fact = dl[i] / dd[i];
+      dl[i] = fact;
+      dd[i + 1] -= fact * du[i];
+    } else {
+      const double fact = dd[i] / dl[i];
+      dd[i] = dl[i];
+      dl[i] = fact;
+      const double tmp = du[i];
+      du[i] = dd[i + 1];
+      dd[i + 1] = tmp - fact * dd[i + 1];
+      if (i < N - 2) {
+        du2[i] = du[i + 1];
+        du[i + 1] = -fact * du[i + 1];
+      }
+      piv[i] = true;
+    }
+  }
+  if (dd[N - 1] == 0.0) dd[N - 1] = eps * tnorm;
+  double x[N];
+  {
+    double nn = 0.0;
+    for (int j = 0; j < N; ++j) {
+      x[j] = (double)((j * 7 + sub * 3) % 5 - 2) + 0.37 * (sub + 1);
+      nn += x[j] * x[j];
+    }
+    const double inv = rsqrt(nn);
+    for (int j = 0; j < N; ++j) x[j] *= inv;
+  }
+  for (int it = 0; it < 3; ++it) {
     for (int i = 0; i < N - 1; ++i) {
-      if (fabs(dd[i]) >= fabs(dl[i])) {
-        if (dd[i] == 0.0) dd[i] = eps * tnorm;
-        const double fact = dl[i] / dd[i];
-        dl[i] = fact;
-        dd[i + 1] -= fact * du[i];
+      if (!piv[i]) {
+        x[i + 1] -= dl[i] * x[i];
       } else {
-        const double fact = dd[i] / dl[i];
-        dd[i] = dl[i];
-        dl[i] = fact;
-        const double tmp = du[i];
-        du[i] = dd[i + 1];
-        dd[i + 1] = tmp - fact * dd[i + 1];
-        if (i < N - 2) {
-          du2[i] = du[i + 1];
-          du[i + 1] = -fact * du[i + 1];
-        }
-        piv[i] = true;
+        const double tmp = x[i];
+        x[i] = x[i + 1];
+        x[i + 1] = tmp - dl[i] * x[i];
       }
     }
-    if (dd[N - 1] == 0.0) dd[N - 1] = eps * tnorm;
-    double x[N];
-    {
+    x[N - 1] /= dd[N - 1];
+    x[N - 2] = (x[N - 2] - du[N - 2] * x[N - 1]) / dd[N - 2];
+    for (int i = N - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / dd[i];
+    {  // scale before the exchange (the solve amplifies by ~1/|lambda - l|)
       double nn = 0.0;
-      for (int j = 0; j < N; ++j) {
-        x[j] = (double)((j * 7 + k * 3) % 5 - 2) + 0.37 * (k + 1);
-        nn += x[j] * x[j];
-      }
-      const double inv = rsqrt(nn);
-      for (int j = 0; j < N; ++j) x[j] *= inv;
-    }
-    for (int it = 0; it < 3; ++it) {
-      for (int i = 0; i < N - 1; ++i) {
-        if (!piv[i]) {
-          x[i + 1] -= dl[i] * x[i];
-        } else {
-          const double tmp = x[i];
-          x[i] = x[i + 1];
-          x[i + 1] = tmp - dl[i] * x[i];
-        }
-      }
-      x[N - 1] /= dd[N - 1];
-      x[N - 2] = (x[N - 2] - du[N - 2] * x[N - 1]) / dd[N - 2];
-      for (int i = N - 3; i >= 0; --i) x[i] = (x[i] - du[i] * x[i + 1] - du2[i] * x[i + 2]) / dd[i];
-      for (int j = 0; j < k; ++j) {  // out[j] temporarily holds the tridiagonal-basis vectors
-        double dot = 0.0;
-        for (int i = 0; i < N; ++i) dot += x[i] * out[j][i];
-        for (int i = 0; i < N; ++i) x[i] -= dot * out[j][i];
-      }
-      double nn = 0.0;
-      for (int i = 0; i < N; ++i) nn += x[i] * x[i];
-      const double inv = nn > 0.0 ? rsqrt(nn) : 0.0;
+      for (int i = 0; i < N; ++i) nn = fmax(nn, fabs(x[i]));
+      const double inv = nn > 0.0 ? 1.0 / nn : 0.0;
       for (int i = 0; i < N; ++i) x[i] *= inv;
     }
-    for (int i = 0; i < N; ++i) out[k][i] = x[i];
-  }
-  for (int k = 0; k < 4; ++k) {  // v = Q y = H_{N-1} ... H_1 y
-    for (int m = 1; m < N; ++m) {
-      if (hs[m] != 0.0) {
+    __syncwarp(gmask);
+    for (int j = 0; j < 4; ++j)
+      for (int i = 0; i < N; ++i) out[j][i] = __shfl_sync(gmask, x[i], gbase + j);
+    for (int k = 0; k < 4; ++k) {  // modified Gram-Schmidt in eigenvalue order
+      for (int j = 0; j < k; ++j) {
         double dot = 0.0;
-        for (int i = 0; i < m; ++i) dot += V[i][m] * out[k][i];
-        dot /= hs[m];
-        for (int i = 0; i < m; ++i) out[k][i] -= dot * V[i][m];
+        for (int i = 0; i < N; ++i) dot += out[k][i] * out[j][i];
+        for (int i = 0; i < N; ++i) out[k][i] -= dot * out[j][i];
       }
+      double nn = 0.0;
+      for (int i = 0; i < N; ++i) nn += out[k][i] * out[k][i];
+      const double inv = nn > 0.0 ? rsqrt(nn) : 0.0;
+      for (int i = 0; i < N; ++i) out[k][i] *= inv;
+    }
+    for (int k = 0; k < 4; ++k)
+      if (k == sub)
+        for (int i = 0; i < N; ++i) x[i] = out[k][i];
+  }
+  for (int m = 1; m < N; ++m) {  // v = Q y = H_{N-1} ... H_1 y, own vector only
+    if (hs[m] != 0.0) {
+      double dot = 0.0;
+      for (int i = 0; i < m; ++i) dot += V(i, m) * x[i];
+      dot /= hs[m];
+      for (int i = 0; i < m; ++i) x[i] -= dot * V(i, m);
     }
   }
+  __syncwarp(gmask);
+  for (int j = 0; j < 4; ++j)
+    for (int i = 0; i < N; ++i) out[j][i] = __shfl_sync(gmask, x[i], gbase + j);
 }
 
 // RANSACUpdateNumIters (App. B.6)
@@ -1258,8 +1296,13 @@ __device__ int update_num_iters(double p, double ep, int max_iters) {
 }
 
 // EPnP on n points in float64, OpenCV's sequence (epnp::compute_pose).
+// Runs on the 4 lanes of a frame's group (identical inputs on every lane): MtM is accumulated over
+// the lane's share of the points and summed with shuffles, the eigenvectors are split over the
+// lanes, and the three beta variants run one per lane (lane 3 repeats variant 3).
+template <typename Mat>
 __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], const Camera& cam, double (&Rbest)[3][3],
-                         double (&tbest)[3]) {
+                         double (&tbest)[3], int sub, unsigned gmask, Mat mtm) {
+  const int gbase = (threadIdx.x & 31) & ~3;
   const double fu = cam.fx, fv = cam.fy, uc = cam.cx, vc = cam.cy;
   double us[kMaxLandmarks][2], al[kMaxLandmarks][4];
   for (int i = 0; i < n; ++i) {
@@ -1290,20 +1333,30 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
     for (int j = 0; j < 3; ++j) al[i][1 + j] = (cov[3 * j] * q[0] + cov[3 * j + 1] * q[1] + cov[3 * j + 2] * q[2]) * inv_k[j];
     al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
   }
-  // MtM (12x12), accumulated row pair by row pair
-  double mtm[12][12] = {};
-  for (int i = 0; i < n; ++i) {
+  // MtM (12x12): upper triangle over this lane's points, summed over the group, mirrored
+  for (int r = 0; r < 12; ++r)
+    for (int c = 0; c < 12; ++c) mtm(r, c) = 0.0;
+  for (int i = sub; i < n; i += 4) {
     double r1[12], r2[12];
     for (int j = 0; j < 4; ++j) {
       r1[3 * j] = al[i][j] * fu, r1[3 * j + 1] = 0.0, r1[3 * j + 2] = al[i][j] * (uc - us[i][0]);
       r2[3 * j] = 0.0, r2[3 * j + 1] = al[i][j] * fv, r2[3 * j + 2] = al[i][j] * (vc - us[i][1]);
     }
     for (int r = 0; r < 12; ++r)
-      for (int c = 0; c < 12; ++c) mtm[r][c] += r1[r] * r1[c] + r2[r] * r2[c];
+      for (int c = r; c < 12; ++c) mtm(r, c) += r1[r] * r1[c] + r2[r] * r2[c];
   }
+  __syncwarp(gmask);
+  for (int r = 0; r < 12; ++r)
+    for (int c = r; c < 12; ++c) {
+      double x = mtm(r, c);
+      x += __shfl_xor_sync(gmask, x, 1);
+      x += __shfl_xor_sync(gmask, x, 2);
+      mtm(r, c) = x;
+      mtm(c, r) = x;
+    }
   // eigenvectors of MtM for the four smallest eigenvalues: v0 = smallest (OpenCV's ut[11]) ... v3
   double v[4][12];
-  sym_eig_smallest4<12>(mtm, v);
+  sym_eig_smallest4<12, Mat>(mtm, v, sub, gmask);
   double L[6][10], rho[6];
   build_L<double>(v, L);
   build_rho<double>(cws, rho);
@@ -1313,8 +1366,9 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
     for (int c = 0; c < 3; ++c) pw0[c] += pw[i][c];
   for (int c = 0; c < 3; ++c) pw0[c] /= n;
 
-  double best_err = 0.0;
-  for (int variant = 1; variant <= 3; ++variant) {
+  double R[3][3], t[3], err;
+  {
+    const int variant = sub < 3 ? sub + 1 : 3;
     double be[4];
     approx_betas<double>(L, rho, variant, be);
     gauss_newton<double>(L, rho, be);
@@ -1336,7 +1390,6 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) abt[r][c] += (pc[r] - pc0[r]) * (pw[i][c] - pw0[c]);
     }
-    double R[3][3], t[3];
     procrustes_uvt<double>(abt, R);
     for (int r = 0; r < 3; ++r) t[r] = pc0[r] - (R[r][0] * pw0[0] + R[r][1] * pw0[1] + R[r][2] * pw0[2]);
     double sum = 0;
@@ -1347,15 +1400,17 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
       const double du = us[i][0] - (uc + fu * Xc * iz), dv = us[i][1] - (vc + fv * Yc * iz);
       sum += sqrt(du * du + dv * dv);
     }
-    const double err = sum / n;
-    // N = 1; if (err2 < err1) N = 2; if (err3 < err[N]) N = 3
-    if (variant == 1 || err < best_err) {
-      best_err = err;
-      for (int r = 0; r < 3; ++r) {
-        for (int c = 0; c < 3; ++c) Rbest[r][c] = R[r][c];
-        tbest[r] = t[r];
-      }
-    }
+    err = sum / n;
+  }
+  // N = 1; if (err2 < err1) N = 2; if (err3 < err[N]) N = 3 — then everybody takes lane N-1's pose
+  __syncwarp(gmask);
+  const double e1 = __shfl_sync(gmask, err, gbase), e2 = __shfl_sync(gmask, err, gbase + 1), e3 = __shfl_sync(gmask, err, gbase + 2);
+  int N = 0;
+  if (e2 < e1) N = 1;
+  if (e3 < (N == 1 ? e2 : e1)) N = 2;
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) Rbest[r][c] = __shfl_sync(gmask, R[r][c], gbase + N);
+    tbest[r] = __shfl_sync(gmask, t[r], gbase + N);
   }
 }
 
@@ -1492,15 +1547,21 @@ __device__ void refine_lm_f64(int n, const double (*pw)[3], const double (*img)[
   }
 }
 
-// The kernel is serial-latency bound: its duration is the time ONE thread needs for its frame
-// (~100 k dependent-ish float64 instructions), whatever the batch size.  `fpw` (frames per warp,
-// dev knob SPE_REFIT_FPW) was swept 32/16/8/4/2 on B200: 2.09/2.09/2.10/2.31/2.82 ms per step,
-// i.e. spreading frames over more warps buys nothing; shortening the chain is the lever.
-__global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int fpw) {
-  const int lane = threadIdx.x & 31, warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (lane >= fpw) return;
-  const int b = warp * fpw + lane;
-  if (b >= a.B) return;
+// The kernel is serial-latency bound: its duration is the time ONE frame's dependent chain of
+// float64 instructions takes, whatever the batch size (spreading whole frames over more warps was
+// measured to buy nothing).  What shortens it is splitting a frame over lanes: every frame gets a
+// group of 4 lanes that run the sequential parts redundantly and share MtM accumulation, the four
+// eigenvectors and the three beta variants (see epnp_f64).
+// kSmemMat: keep the 12x12 working matrix in shared memory (36 KB per 32-thread CTA: lowest latency
+// when the kernel has the GPU to itself) or in local memory (no shared-memory footprint: the
+// variant used when it runs as a background tail under the next batch's hypothesis kernel, whose
+// three CTAs per SM leave no room for 36 KB more).
+template <bool kSmemMat>
+__global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws) {
+  const int lane = threadIdx.x & 31, sub = lane & 3;
+  const unsigned gmask = 0xFu << (lane & ~3);
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  if (b >= a.B) return;  // whole groups leave together (blockDim is a multiple of 4)
   const int n = ws.n[b];
   const unsigned vis = ws.vis[b];
   int status = SPE_FRAME_OK, winner = -1;
@@ -1543,9 +1604,16 @@ __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, Rans
         und[k][1] = n == kModelPoints ? (double)(float)q.y : q.y;
         ++k;
       }
-    epnp_f64(k, pw, und, m.cam, R, t);
+    if constexpr (kSmemMat) {
+      extern __shared__ double s_mat[];  // [144][blockDim.x]
+      epnp_f64(k, pw, und, m.cam, R, t, sub, gmask, SmemMat12{s_mat + threadIdx.x, (int)blockDim.x});
+    } else {
+      double mtm[12][12];
+      epnp_f64(k, pw, und, m.cam, R, t, sub, gmask, LocalMat12{mtm});
+    }
     if (a.refine_lm) refine_lm_f64(k, pw, img, m.cam, R, t);
   }
+  if (sub != 0) return;
   double q[4] = {1, 0, 0, 0};
   if (status == SPE_FRAME_OK) rotation_to_quat(R, q);
   float* o = a.pose7 + (size_t)b * 7;
@@ -1618,20 +1686,21 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
 cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
   DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam};
-  const int fpw = a.refit_frames_per_warp;
-  // Without this the kernel (no shared memory of its own) flips idle SMs to an all-L1 split and the
-  // next batch's decode CTAs must wait for it to finish: measured 0.12 -> 0.32 ms decode when overlapped.
+  // Without a common carveout the kernel flips idle SMs to an all-L1 split and the next batch's
+  // decode CTAs must wait for it to finish: measured 0.12 -> 0.32 ms decode when overlapped.
   static PerDeviceOnce once;
-  const cudaError_t ce =
-      once.run(m.device, [] { return cudaFuncSetAttribute(select_refit_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct); });
+  const cudaError_t ce = once.run(m.device, [] {
+    cudaError_t r = cudaFuncSetAttribute(select_refit_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(select_refit_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    return r;
+  });
   if (ce != cudaSuccess) return ce;
-  static int wpb = [] {
-    const char* v = getenv("SPE_REFIT_WPB");  // dev knob: warps per CTA
-    const int w = v ? atoi(v) : 1;
-    return w >= 1 && w <= 4 ? w : 1;
-  }();
-  const int warps = (a.B + fpw - 1) / fpw;
-  select_refit_kernel<<<(warps + wpb - 1) / wpb, wpb * 32, 0, stream>>>(dm, a, ws, fpw);
+  const int ctas = (a.B + 7) / 8;  // 4 lanes per frame, one warp per CTA
+  if (a.refit_background) {
+    select_refit_kernel<false><<<ctas, 32, 0, stream>>>(dm, a, ws);
+  } else {
+    select_refit_kernel<true><<<ctas, 32, sizeof(double) * 144 * 32, stream>>>(dm, a, ws);
+  }
   return cudaGetLastError();
 }
 

@@ -248,7 +248,7 @@ class StreamedHeatmapToPose:
         _lib.check(self._L.spe_ransac_select_refit_f32(st.solver.handle, B, st.hypotheses, st.confidence, out.pose7.data_ptr(),
                                                        out.inlier_mask.data_ptr(), out.status.data_ptr(), None,
                                                        slot["rt"].data_ptr() if slot["rt"] is not None else None, ws.data_ptr(), ws.numel(),
-                                                       st.flags, side.cuda_stream), "spe_ransac_select_refit_f32")
+                                                       st.flags | _lib.FLAG_BACKGROUND_TAIL, side.cuda_stream), "spe_ransac_select_refit_f32")
         if self.gather_total is not None:
             with torch.cuda.stream(side):
                 slot["gathered"] = all_gather_rows(out.pose7, self.gather_total)
