@@ -80,3 +80,20 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert not re.search(r"^\s*(from|import)\s+cv2\b", src, flags=re.M), f"{f} must not depend on OpenCV"
+
+
+def test_pose_entry_points_validate_arguments_without_gpu(lib):
+    """No model can exist without a GPU, so every pose entry point must reject a NULL model (and
+    the combined decode its argument errors) before touching CUDA."""
+    assert lib.spe_ransac_epnp_f32(None, None, 4, 64, 15.0, 0.99, -1.0, None, None, None, None, None, None, 0, 0, None) == -1
+    assert lib.spe_ransac_score_f32(None, None, 4, 64, 15.0, 0.99, -1.0, None, 0, 0, None) == -1
+    assert lib.spe_ransac_select_refit_f32(None, 4, 64, 0.99, None, None, None, None, None, None, 0, 0, None) == -1
+    assert lib.spe_heatmap_to_pose_f32(None, None, 4, 11, 64, 64, None, None, 1, 64, 15.0, 0.99, -1.0, None, None, None, None, None, 0, 0, None) == -1
+    assert lib.spe_pipeline_workspace_bytes(None, 4, 11, 64) == 0
+    assert lib.spe_pnp_model_num_landmarks(None) == -1
+    ptrs = (ctypes.c_void_p * 2)(None, None)
+    assert lib.spe_decode_combined_kpts_f32(ptrs, 0, 0, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # K < 1
+    assert lib.spe_decode_combined_kpts_f32(ptrs, 9, 0, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # K > 8
+    assert lib.spe_decode_combined_kpts_f32(ptrs, 3, 1, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # flip needs K == 2
+    assert lib.spe_decode_combined_kpts_f32(ptrs, 2, 7, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # unknown mode
+    assert lib.spe_decode_combined_kpts_f32(ptrs, 2, 0, None, 0, 0, 11, 64, 64, None, None, 1, None, None, None) == 0  # empty batch
