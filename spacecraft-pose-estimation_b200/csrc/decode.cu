@@ -313,6 +313,95 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_bulk_kernel(const Decod
 }
 
 // ------------------------------------------------------------------------------------------
+// Team variant for FEW, LARGE maps (the reference's 384x384 / 768x768 heatmaps at small batch):
+// with one warp per map a batch of 8 x 11 maps would keep 13 SMs busy.  Here a CTA owns a map, its
+// warps stream interleaved 16 KB chunks of it (same bulk-copy + mbarrier mechanics, one stage per
+// warp), and the per-warp (max, first index) results meet in shared memory.
+template <int kWarps, int kChunk>
+__global__ void __launch_bounds__(kWarps * 32, 1) decode_team_kernel(const DecodeArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kChunk;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWarps * kChunk * sizeof(float)) + warp;
+  Best* team = reinterpret_cast<Best*>(smem_raw + (size_t)kWarps * kChunk * sizeof(float) + kWarps * sizeof(uint64_t));
+
+  const int hw = a.H * a.W;
+  const int chunks_per_map = (hw + kChunk - 1) / kChunk;
+  const int my_per_map = (chunks_per_map - warp + kWarps - 1) / kWarps;  // >= 1: the launcher requires chunks_per_map >= kWarps
+  const int my_maps = (a.n_maps > (int)blockIdx.x) ? (a.n_maps - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long my_chunks = (long long)my_maps * my_per_map;
+
+  if (lane == 0) {
+    mbar_init(smem_u32(bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint64_t policy = evict_first_policy();
+  auto issue = [&](long long c) {  // lane 0 only
+    const int mi = (int)(c / my_per_map), k = (int)(c - (long long)mi * my_per_map);
+    const int map = blockIdx.x + mi * gridDim.x;
+    const int off = (warp + k * kWarps) * kChunk;
+    const int n = min(kChunk, hw - off);
+    mbar_expect_tx(smem_u32(bar), (uint32_t)n * 4u);
+    bulk_g2s(smem_u32(stage), a.hm + (size_t)map * hw + off, (uint32_t)n * 4u, smem_u32(bar), policy);
+  };
+  if (lane == 0 && my_chunks > 0) issue(0);
+
+  Best acc[4];
+  long long c = 0;
+  for (int mi = 0; mi < my_maps; ++mi) {
+    const int map = blockIdx.x + mi * gridDim.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[k] = Best{-INFINITY, kNoIndex};
+    int first_elem = kNoIndex;  // first element this lane owns in this map (for all -inf maps)
+    for (int k = 0; k < my_per_map; ++k, ++c) {
+      const int off = (warp + k * kWarps) * kChunk;
+      const int n = min(kChunk, hw - off);
+      mbar_wait(smem_u32(bar), (uint32_t)(c & 1));
+      const int nvec = n >> 2;
+      const float4* v4 = reinterpret_cast<const float4*>(stage);
+      int ebase = off + 4 * lane;
+      if (first_elem == kNoIndex && lane < nvec) first_elem = ebase;
+#pragma unroll 4
+      for (int v = lane; v < nvec; v += 32, ebase += 128) {
+        const float4 q = v4[v];
+        take(acc[0], q.x, ebase);
+        take(acc[1], q.y, ebase);
+        take(acc[2], q.z, ebase);
+        take(acc[3], q.w, ebase);
+      }
+      __syncwarp();
+      if (lane == 0 && c + 1 < my_chunks) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(c + 1);
+      }
+    }
+    Best b{-INFINITY, kNoIndex};
+    if (first_elem != kNoIndex) {
+      b = Best{acc[0].v, acc[0].i == kNoIndex ? first_elem : acc[0].i};
+#pragma unroll
+      for (int k = 1; k < 4; ++k) merge(b, acc[k].v, (acc[k].i == kNoIndex ? first_elem : acc[k].i) + k);
+    }
+    b = warp_merge(b);
+    if (lane == 0) team[warp] = b;
+    __syncthreads();
+    if (warp == 0) {
+      Best t = lane < kWarps ? team[lane] : Best{-INFINITY, kNoIndex};
+      t = warp_merge(t);
+      const float* g = a.hm + (size_t)map * hw;
+      if (t.v != t.v) t.i = first_nan_index(g, hw, lane);
+      if (lane == 0) {
+        const float* gi = g + t.i;
+        finish_map(a, map, t.v, t.i, [&](float& l, float& r, float& u, float& d) {
+          l = __ldg(gi - 1), r = __ldg(gi + 1), u = __ldg(gi - a.W), d = __ldg(gi + a.W);
+        });
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Fallback for maps that are not 16-byte aligned: warp per map, coalesced scalar loads.
 constexpr int kPlainWarps = 4;
 
@@ -488,6 +577,25 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
   if (de != cudaSuccess) return de;
   const long long hw = (long long)a.H * a.W;
   const bool aligned = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.hm) & 15u) == 0);
+  {
+    // few large maps: one CTA per map instead of one warp per map
+    constexpr int kTeamWarps = 7, kTeamChunk = 4096;
+    const long long chunks_per_map = (hw + kTeamChunk - 1) / kTeamChunk;
+    if (aligned && decode_variant() == 0 && chunks_per_map >= kTeamWarps && a.n_maps < num_sms * kTeamWarps) {
+      constexpr size_t smem = (size_t)kTeamWarps * kTeamChunk * sizeof(float) + kTeamWarps * (sizeof(uint64_t) + sizeof(Best));
+      static PerDeviceOnce once;
+      cudaError_t e = once.run(dev, [] {
+        cudaError_t r = cudaFuncSetAttribute(decode_team_kernel<kTeamWarps, kTeamChunk>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (r == cudaSuccess)
+          r = cudaFuncSetAttribute(decode_team_kernel<kTeamWarps, kTeamChunk>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+        return r;
+      });
+      if (e != cudaSuccess) return e;
+      const int grid = a.n_maps < num_sms ? a.n_maps : num_sms;
+      decode_team_kernel<kTeamWarps, kTeamChunk><<<grid, kTeamWarps * 32, smem, stream>>>(a);
+      return cudaGetLastError();
+    }
+  }
   if (aligned) {
     switch (decode_variant()) {
       case 1: return launch_bulk<4, 3, 4096>(a, dev, num_sms, stream);   // 192 KB, 4 warps
