@@ -159,15 +159,18 @@ size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypothese
 
 static int hyp_kernel_setting() {
   static int variant = [] {
-    const char* v = getenv("SPE_HYP_KERNEL");  // dev knob: "g4" = 4 lanes per hypothesis
-    return (v && v[0] == 'g') ? 1 : 0;
+    // dev knob for A/B runs: "g4" = 4 lanes per hypothesis, "jacobi" = thread per hypothesis with the full
+    // one-sided Jacobi SVD of M^T; default = thread per hypothesis, Householder QR + inverse iteration
+    const char* v = getenv("SPE_HYP_KERNEL");
+    return (v && v[0] == 'g') ? 1 : (v && v[0] == 'j') ? 2 : 0;
   }();
   return variant;
 }
 
 static int jacobi_sweeps_setting() {
   static int sweeps = [] {
-    const char* v = getenv("SPE_JACOBI_SWEEPS");  // dev knob
+    // dev knob: Jacobi sweeps (variants 1, 2) or inverse-iteration steps (variant 0)
+    const char* v = getenv(hyp_kernel_setting() == 0 ? "SPE_EIG_ITERS" : "SPE_JACOBI_SWEEPS");
     const int dflt = hyp_kernel_setting() == 1 ? 5 : 6;
     const int s = v ? atoi(v) : dflt;
     return s > 0 && s <= 30 ? s : dflt;

@@ -50,11 +50,11 @@ struct RansacArgs {
   float reproj_err;
   double confidence;
   float conf_floor;  // < 0: the reference's adaptive filter
-  int jacobi_sweeps;
+  int jacobi_sweeps;  // Jacobi sweeps (variants 1, 2) / inverse-iteration steps (variant 0)
   int refine_lm;              // SPE_FLAG_REFINE_LM
   int adaptive;               // SPE_FLAG_ADAPTIVE: score only the hypotheses cv2 could look at
   int refit_background;       // the tail runs under other kernels: keep its shared-memory footprint at zero
-  int kernel_variant;  // 0: thread per hypothesis (default), 1: 4 lanes per hypothesis
+  int kernel_variant;  // 0: thread per hypothesis, QR + inverse iteration (default); 1: 4 lanes per hypothesis; 2: thread per hypothesis, Jacobi SVD
   float* pose7;           // [B,7]
   uint32_t* inlier_mask;  // [B]
   int32_t* status;        // [B]

@@ -654,6 +654,171 @@ __device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], in
   fold_and_norms(A, w, d);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// The same four vectors without a full SVD (default; the Jacobi above stays selectable with
+// SPE_HYP_KERNEL=jacobi for A/B runs).  EPnP needs the four smallest right singular directions of
+// the 10 x 12 matrix M only:
+//   * v0, v1 span the exact null space.  Householder QR of A = M^T (12 x 10, in place: R in the upper
+//     triangle, the reflectors below it) gives it for free: the last two columns of Q;
+//   * v2, v3 belong to the two smallest singular values of R (M^T M = Q R R^T Q^T): block inverse
+//     iteration x <- R^-T R^-1 x on two vectors (two triangular solves each, Gram-Schmidt every
+//     step), a 2 x 2 Rayleigh-Ritz rotation to separate them, then v = Q [w; 0; 0].
+// The bottom of M's spectrum is strongly graded for a perspective camera metres away from a
+// sub-metre target (sigma_2 / sigma_3 ~ 0.15 median on the benchmark data), so the iteration reaches
+// FP32 noise in 4-6 steps; where it has not (close range, sigma_3 ~ sigma_4) v3 is a mixture inside an
+// almost degenerate pair, which is as arbitrary in OpenCV's own SVD.  Checked against cv2 with the
+// NumPy model tools/proto_eig.py before it was written and on the GPU afterwards: per-hypothesis
+// inlier-count agreement and winner-mask agreement are the same as with the Jacobi SVD.
+// ~3.7 k instead of ~18 k instructions per hypothesis for this stage.
+__device__ __forceinline__ void eig_qr_inverse_iteration(float (&A)[12][10], float* __restrict__ work, int iters) {
+  // ---- Householder QR, H_k = I - tau_k v_k v_k^T with v_k = (1, A[k+1..11][k]) -----------------
+  // tau_k is parked in work[24 + k] (the v2 slot is free until the very end).
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    float ss = 0.f;
+#pragma unroll
+    for (int i = k + 1; i < 12; ++i) ss = fmaf(A[i][k], A[i][k], ss);
+    const float x0 = A[k][k];
+    const float nn = fmaf(x0, x0, ss);
+    const bool ok = nn > 1e-30f;
+    const float nrm = sqrt_approx(nn);
+    const float v0 = x0 + copysignf(nrm, x0);
+    const float iv0 = ok ? rcp_approx(v0) : 0.f;
+    const float tau = ok ? (fabsf(x0) + nrm) * rcp_approx(nrm) : 0.f;
+    work[24 + k] = tau;
+    A[k][k] = -copysignf(nrm, x0);
+#pragma unroll
+    for (int i = k + 1; i < 12; ++i) A[i][k] *= iv0;
+#pragma unroll
+    for (int j = k + 1; j < 10; ++j) {
+      float s = A[k][j];
+#pragma unroll
+      for (int i = k + 1; i < 12; ++i) s = fmaf(A[i][k], A[i][j], s);
+      s *= tau;
+      A[k][j] -= s;
+#pragma unroll
+      for (int i = k + 1; i < 12; ++i) A[i][j] = fmaf(-s, A[i][k], A[i][j]);
+    }
+  }
+  // y <- Q y = H_0 ( ... (H_9 y))
+  auto apply_q = [&](float (&y)[12]) {
+#pragma unroll
+    for (int k = 9; k >= 0; --k) {
+      float s = y[k];
+#pragma unroll
+      for (int i = k + 1; i < 12; ++i) s = fmaf(A[i][k], y[i], s);
+      s *= work[24 + k];
+      y[k] -= s;
+#pragma unroll
+      for (int i = k + 1; i < 12; ++i) y[i] = fmaf(-s, A[i][k], y[i]);
+    }
+  };
+  // ---- null space: the last two columns of Q ---------------------------------------------------
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float y[12];
+#pragma unroll
+    for (int r = 0; r < 12; ++r) y[r] = r == 10 + c ? 1.0f : 0.0f;
+    apply_q(y);
+#pragma unroll
+    for (int r = 0; r < 12; ++r) work[12 * c + r] = y[r];
+  }
+  // ---- block inverse iteration on R R^T ---------------------------------------------------------
+  float rinv[10];
+  {
+    float rmax = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rmax = fmaxf(rmax, fabsf(A[i][i]));
+    const float floor_ = fmaxf(rmax * 1e-7f, 1e-30f);  // a numerically zero pivot: keep the solves finite
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rinv[i] = rcp_approx(copysignf(fmaxf(fabsf(A[i][i]), floor_), A[i][i]));
+  }
+  float w0[10] = {1.0f, -0.7f, 0.5f, 0.9f, -0.4f, 0.8f, -0.6f, 0.3f, -0.95f, 0.65f};
+  float w1[10] = {0.6f, 0.85f, -0.45f, 0.35f, 0.75f, -0.9f, -0.5f, 0.55f, 0.4f, -0.8f};
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    // R a = w (back substitution), in place
+#pragma unroll
+    for (int i = 9; i >= 0; --i) {
+      float a0 = w0[i], a1 = w1[i];
+#pragma unroll
+      for (int j = i + 1; j < 10; ++j) {
+        a0 = fmaf(-A[i][j], w0[j], a0);
+        a1 = fmaf(-A[i][j], w1[j], a1);
+      }
+      w0[i] = a0 * rinv[i];
+      w1[i] = a1 * rinv[i];
+    }
+    // R^T y = a (forward substitution), in place
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      float a0 = w0[i], a1 = w1[i];
+#pragma unroll
+      for (int j = 0; j < i; ++j) {
+        a0 = fmaf(-A[j][i], w0[j], a0);
+        a1 = fmaf(-A[j][i], w1[j], a1);
+      }
+      w0[i] = a0 * rinv[i];
+      w1[i] = a1 * rinv[i];
+    }
+    // Gram-Schmidt
+    float n0 = 0.f, d01 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      n0 = fmaf(w0[i], w0[i], n0);
+      d01 = fmaf(w0[i], w1[i], d01);
+    }
+    const float i0 = rsqrt_approx(fmaxf(n0, 1e-30f));
+    const float proj = d01 * i0 * i0;
+    float n1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      w1[i] = fmaf(-proj, w0[i], w1[i]);
+      w0[i] *= i0;
+      n1 = fmaf(w1[i], w1[i], n1);
+    }
+    const float i1 = rsqrt_approx(fmaxf(n1, 1e-30f));
+#pragma unroll
+    for (int i = 0; i < 10; ++i) w1[i] *= i1;
+  }
+  // ---- Rayleigh-Ritz inside the pair: S = W^T R R^T W, rotate so that S is diagonal ---------------
+  {
+    float s00 = 0.f, s01 = 0.f, s11 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      float g0 = 0.f, g1 = 0.f;
+#pragma unroll
+      for (int k = 0; k <= j; ++k) {
+        g0 = fmaf(A[k][j], w0[k], g0);
+        g1 = fmaf(A[k][j], w1[k], g1);
+      }
+      s00 = fmaf(g0, g0, s00);
+      s01 = fmaf(g0, g1, s01);
+      s11 = fmaf(g1, g1, s11);
+    }
+    const float h = s11 - s00, gg = s01 + s01;
+    const float q = sqrt_approx(fmaf(h, h, fmaf(gg, gg, 1e-37f)));
+    const float t = gg * rcp_approx(h + copysignf(q, h));
+    const float c = rsqrt_approx(fmaf(t, t, 1.0f)), sn = c * t;
+    const bool swap = fmaf(-t, s01, s00) > fmaf(t, s01, s11);  // v2 = the smaller Ritz value
+    float y2[12], y3[12];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const float a = c * w0[i] - sn * w1[i], b = sn * w0[i] + c * w1[i];
+      y2[i] = swap ? b : a;
+      y3[i] = swap ? a : b;
+    }
+    y2[10] = y2[11] = y3[10] = y3[11] = 0.f;
+    // both back-transforms read tau from work[24..33] before v2 is written over it
+    apply_q(y2);
+    apply_q(y3);
+#pragma unroll
+    for (int r = 0; r < 12; ++r) work[24 + r] = y2[r], work[36 + r] = y3[r];
+  }
+}
+
+template <int kEig>  // 0: Householder QR + inverse iteration (default), 1: one-sided Jacobi SVD of M^T
 __global__ void __maxnreg__(SPE_T1_REGS)
 hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_begin, int hblocks, const int32_t* __restrict__ need,
                      float thr2, int sweeps, RansacWorkspace ws) {
@@ -716,6 +881,9 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
       }
     }
   }
+  if constexpr (kEig == 0) {
+    eig_qr_inverse_iteration(A, work, sweeps);
+  } else {
   jacobi_mt(A, d, sweeps);
 
   // ---- v2, v3 = the two smallest singular directions; v0, v1 = null space (complement) ---------
@@ -811,6 +979,7 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
 #pragma unroll
     for (int r = 0; r < 12; ++r) work[r] = n0[r], work[12 + r] = n1[r];
   }
+  }  // kEig
 
   // ---- the three beta variants, one after the other; keep the best by OpenCV's rule -----------
   float Rb[3][3], tb[3], eb = 0.f;
@@ -1655,15 +1824,23 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
       hypothesis_kernel<<<(unsigned)ctas, kHypPerCta * kGroup, 0, stream>>>(dm, a.kpts, a.H, hblocks, thr2, a.jacobi_sweeps, ws);
     } else {  // one thread per hypothesis, one warp per (frame, 32 hypotheses)
       static PerDeviceOnce once;  // same shared-memory/L1 split as the decode kernel (decode.cuh)
-      e = once.run(m.device, [] { return cudaFuncSetAttribute(hypothesis_kernel_t1, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct); });
+      e = once.run(m.device, [] {
+        cudaError_t r = cudaFuncSetAttribute(hypothesis_kernel_t1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+        if (r == cudaSuccess) r = cudaFuncSetAttribute(hypothesis_kernel_t1<1>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+        return r;
+      });
       if (e != cudaSuccess) return e;
+      const bool jacobi = a.kernel_variant == 2;  // full SVD of M^T (kept for A/B measurements)
       constexpr int kWarps = kT1Threads / 32;
       auto launch = [&](int h_begin, int h_count, const int32_t* need) -> cudaError_t {
         const int hblocks = (h_count + 31) / 32;
         const long long ctas = ((long long)a.B * hblocks + kWarps - 1) / kWarps;
         if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
         if (ctas == 0) return cudaSuccess;
-        hypothesis_kernel_t1<<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
+        if (jacobi)
+          hypothesis_kernel_t1<1><<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
+        else
+          hypothesis_kernel_t1<0><<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
         return cudaGetLastError();
       };
       if (a.adaptive && a.H > kFirstPass) {
