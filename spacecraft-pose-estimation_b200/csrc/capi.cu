@@ -178,6 +178,15 @@ static int jacobi_sweeps_setting() {
   return sweeps;
 }
 
+static int t1_warps_setting() {
+  static int warps = [] {
+    const char* v = getenv("SPE_T1_WARPS");  // dev knob: warps per CTA of the hypothesis kernel
+    const int w = v ? atoi(v) : 4;
+    return w >= 1 && w <= 4 ? w : 4;
+  }();
+  return warps;
+}
+
 static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, void* workspace, size_t workspace_bytes, spe::RansacArgs& a,
                             spe::RansacWorkspace& ws) {
   if (model == nullptr || B < 0 || hypotheses < 1 || hypotheses > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
@@ -194,6 +203,7 @@ static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, voi
   a.H = hypotheses;
   a.jacobi_sweeps = jacobi_sweeps_setting();
   a.kernel_variant = hyp_kernel_setting();
+  a.t1_warps = t1_warps_setting();
   ws = spe::carve_workspace(workspace, model->m.J, B, hypotheses);
   return SPE_OK;
 }

@@ -176,7 +176,9 @@ __device__ __forceinline__ void lsq_normal(const T (&A)[R][C], const T (&b)[R], 
 }
 
 // L (6x10) from the four null-space candidates v[i][0..11] (four 3-vectors each); App. B.3g.
-template <typename T>
+// kDoubledDiag (FP32 hypothesis path): the squared terms are stored doubled too, L[k][{0,2,5,9}] = 2 |d_i|^2,
+// which turns a Gauss-Newton Jacobian row into four plain dot products (gauss_newton_doubled below).
+template <typename T, bool kDoubledDiag = false>
 __device__ __forceinline__ void build_L(const T (&v)[4][12], T (&L)[6][10]) {
   constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
@@ -187,16 +189,17 @@ __device__ __forceinline__ void build_L(const T (&v)[4][12], T (&L)[6][10]) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) d[i][c] = v[i][3 * pa[k] + c] - v[i][3 * pb[k] + c];
     auto dot = [&](int i, int j) { return d[i][0] * d[j][0] + d[i][1] * d[j][1] + d[i][2] * d[j][2]; };
-    L[k][0] = dot(0, 0);
+    constexpr T dg = kDoubledDiag ? T(2) : T(1);
+    L[k][0] = dg * dot(0, 0);
     L[k][1] = T(2) * dot(0, 1);
-    L[k][2] = dot(1, 1);
+    L[k][2] = dg * dot(1, 1);
     L[k][3] = T(2) * dot(0, 2);
     L[k][4] = T(2) * dot(1, 2);
-    L[k][5] = dot(2, 2);
+    L[k][5] = dg * dot(2, 2);
     L[k][6] = T(2) * dot(0, 3);
     L[k][7] = T(2) * dot(1, 3);
     L[k][8] = T(2) * dot(2, 3);
-    L[k][9] = dot(3, 3);
+    L[k][9] = dg * dot(3, 3);
   }
 }
 
@@ -213,7 +216,9 @@ __device__ __forceinline__ void build_rho(const T (&cws)[4][3], T (&rho)[6]) {
 
 // The three linearised initialisations of EPnP (App. B.3h), variant = 1, 2 or 3, as one piece
 // of straight-line code so that lanes running different variants do not diverge.
-template <typename T, bool kNormalEq = false>
+// kDoubledDiag: L comes from build_L<T, true>; a doubled column halves its unknown (exactly, a power
+// of two), which is undone after the solve.
+template <typename T, bool kNormalEq = false, bool kDoubledDiag = false>
 __device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)[6], int variant, T (&betas)[4]) {
   T A[6][5], b[6], x[5];
   const bool v1 = variant == 1, v3 = variant == 3;
@@ -228,6 +233,10 @@ __device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)
   }
   if constexpr (kNormalEq) lsq_normal<T, 6, 5>(A, b, x);  // masked (all-zero) columns come out as x = 0 in both
   else lsq_householder<T, 6, 5>(A, b, x);
+  if constexpr (kDoubledDiag) {
+    x[0] *= T(2);             // column L[.][0]
+    if (!v1) x[2] *= T(2);    // column L[.][2] (variants 2, 3)
+  }
   const bool neg = x[0] < T(0);
   const T b0mag = Real<T>::sqrt(Real<T>::abs(x[0]));
   if (v1) {
@@ -268,6 +277,29 @@ __device__ __forceinline__ void gauss_newton(const T (&L)[6][10], const T (&rho)
     }
     if constexpr (kNormalEq) lsq_normal<T, 6, 4>(A, r, x);
     else lsq_householder<T, 6, 4>(A, r, x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) be[i] += x[i];
+  }
+}
+
+// The same five steps for the FP32 hypothesis path, on L with doubled squared terms (build_L<T, true>):
+// Jacobian row k = four 4-term dot products, and beta^T Q_k beta = (J_k . beta) / 2 gives the residual
+// from it (126 instead of 204 instructions per step).
+__device__ __forceinline__ void gauss_newton_doubled(const float (&L)[6][10], const float (&rho)[6], float (&be)[4]) {
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    float A[6][4], r[6], x[4];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float* l = L[k];
+      A[k][0] = fmaf(l[6], be[3], fmaf(l[3], be[2], fmaf(l[1], be[1], l[0] * be[0])));
+      A[k][1] = fmaf(l[7], be[3], fmaf(l[4], be[2], fmaf(l[2], be[1], l[1] * be[0])));
+      A[k][2] = fmaf(l[8], be[3], fmaf(l[5], be[2], fmaf(l[4], be[1], l[3] * be[0])));
+      A[k][3] = fmaf(l[9], be[3], fmaf(l[8], be[2], fmaf(l[7], be[1], l[6] * be[0])));
+      const float q2 = fmaf(A[k][3], be[3], fmaf(A[k][2], be[2], fmaf(A[k][1], be[1], A[k][0] * be[0])));
+      r[k] = fmaf(-0.5f, q2, rho[k]);
+    }
+    lsq_normal<float, 6, 4>(A, r, x);
 #pragma unroll
     for (int i = 0; i < 4; ++i) be[i] += x[i];
   }

@@ -546,6 +546,9 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
 constexpr int kT1Threads = 128;
 __device__ __forceinline__ int ws_frames(const RansacWorkspace& ws) { return ws.frames; }
 constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alphas[5][4] (+1: odd stride, conflict-free)
+// shared memory of one warp: landmarks [32][3], ideal + raw pixels [32] float2 each, per-thread scratch
+constexpr int kT1WarpBytes = (int)(sizeof(float) * 3 * kMaxLandmarks + 2 * sizeof(float2) * kMaxLandmarks + sizeof(float) * 32 * kT1Stride);
+static_assert(kT1WarpBytes % 16 == 0, "per-warp shared-memory slice must stay 16-byte aligned");
 
 // One Jacobi rotation between the columns at register positions P and Q of A, with the two
 // columns SWAPPED on output.  With the swap built in, the odd-even ordering below brings every
@@ -824,13 +827,16 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
                      float thr2, int sweeps, RansacWorkspace ws) {
   // One warp = one work item: 32 consecutive hypotheses [h_begin + 32*hb, +32) of frame b.  Warps of
   // a CTA are independent (different frames in general), each with its own copy of the frame data.
-  constexpr int kWarps = kT1Threads / 32;
-  __shared__ float s_pw_all[kWarps][kMaxLandmarks][3];
-  __shared__ float2 s_us_all[kWarps][kMaxLandmarks];
-  __shared__ float2 s_img_all[kWarps][kMaxLandmarks];
-  __shared__ float s_work[kT1Threads][kT1Stride];
-
+  // Warps are independent, each with its own slice of (dynamic) shared memory, so the CTA size is a
+  // launch-time choice (launch_ransac_score): small CTAs pack around the previous batch's refit CTAs.
+  extern __shared__ __align__(16) unsigned char t1_smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int kWarps = blockDim.x >> 5;
+  unsigned char* const wbase = t1_smem + (size_t)warp * kT1WarpBytes;
+  float(*s_pw)[3] = reinterpret_cast<float(*)[3]>(wbase);
+  float2* s_us = reinterpret_cast<float2*>(wbase + sizeof(float) * 3 * kMaxLandmarks);
+  float2* s_img = s_us + kMaxLandmarks;
+  float* work = reinterpret_cast<float*>(s_img + kMaxLandmarks) + lane * kT1Stride;
   const long long item = (long long)blockIdx.x * kWarps + warp;
   const int b = (int)(item / hblocks), hb = (int)(item - (long long)b * hblocks);
   if (b >= ws_frames(ws)) return;
@@ -841,9 +847,6 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
   const int limit = need ? min(need[b], H) : H;
   if (h_begin + hb * 32 >= limit) return;
   const unsigned vis = ws.vis[b];
-  float(*s_pw)[3] = s_pw_all[warp];
-  float2* s_us = s_us_all[warp];
-  float2* s_img = s_img_all[warp];
   if (lane < n) {
     const int j = __fns(vis, 0, lane + 1);
     s_pw[lane][0] = m.landmarks[3 * j], s_pw[lane][1] = m.landmarks[3 * j + 1], s_pw[lane][2] = m.landmarks[3 * j + 2];
@@ -857,7 +860,6 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
   int si[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) si[k] = sub[k];
-  float* work = s_work[tid];
   const float fu = (float)m.cam.fx, fv = (float)m.cam.fy, uc = (float)m.cam.cx, vc = (float)m.cam.cy;
 
   // ---- control points, alphas, M^T ---------------------------------------------------------
@@ -991,7 +993,13 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 12; ++j) v[i][j] = work[12 * i + j];
-      build_L<float>(v, L);
+      build_L<float, true>(v, L);
+      // computed ONCE: without the barrier the compiler sinks the 60 entries into the variant loop
+      // below and recomputes them three times (ncu source page, profiles/solver_r1.md)
+#pragma unroll
+      for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int i = 0; i < 10; ++i) asm volatile("" : "+f"(L[k][i]));
     }
     float pw[5][3], pw0[3] = {0.f, 0.f, 0.f};
 #pragma unroll
@@ -1006,8 +1014,8 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
 #pragma unroll 1
     for (int variant = 1; variant <= 3; ++variant) {
       float betas[4];
-      approx_betas<float, true>(L, rho, variant, betas);
-      gauss_newton<float, true>(L, rho, betas);
+      approx_betas<float, true, true>(L, rho, variant, betas);
+      gauss_newton_doubled(L, rho, betas);
       float ccs[4][3];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
@@ -1831,16 +1839,17 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
       });
       if (e != cudaSuccess) return e;
       const bool jacobi = a.kernel_variant == 2;  // full SVD of M^T (kept for A/B measurements)
-      constexpr int kWarps = kT1Threads / 32;
+      const int kWarps = a.t1_warps >= 1 && a.t1_warps <= 4 ? a.t1_warps : 4;
+      const size_t smem = (size_t)kWarps * kT1WarpBytes;
       auto launch = [&](int h_begin, int h_count, const int32_t* need) -> cudaError_t {
         const int hblocks = (h_count + 31) / 32;
         const long long ctas = ((long long)a.B * hblocks + kWarps - 1) / kWarps;
         if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
         if (ctas == 0) return cudaSuccess;
         if (jacobi)
-          hypothesis_kernel_t1<1><<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
+          hypothesis_kernel_t1<1><<<(unsigned)ctas, kWarps * 32, smem, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
         else
-          hypothesis_kernel_t1<0><<<(unsigned)ctas, kT1Threads, 0, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
+          hypothesis_kernel_t1<0><<<(unsigned)ctas, kWarps * 32, smem, stream>>>(dm, a.kpts, a.H, h_begin, hblocks, need, thr2, a.jacobi_sweeps, ws);
         return cudaGetLastError();
       };
       if (a.adaptive && a.H > kFirstPass) {
