@@ -40,7 +40,7 @@ struct Real<float> {
   static __device__ __forceinline__ float copysign(float m, float s) { return copysignf(m, s); }
   static constexpr float eps = 1.1920929e-7f;
   static constexpr float tiny = 1e-30f;
-  static constexpr int svd3_sweeps = 5;
+  static constexpr int svd3_sweeps = 4;  // converged to rounding in 4 (200k random FP32 cases, worst |dR| 2.6e-6)
 };
 template <>
 struct Real<double> {

@@ -261,7 +261,7 @@ __device__ __forceinline__ void control_points5(const float (&pw)[5][3], float (
 #pragma unroll
     for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.f : 0.f;
 #pragma unroll 1
-  for (int sweep = 0; sweep < 5; ++sweep) {
+  for (int sweep = 0; sweep < Real<float>::svd3_sweeps; ++sweep) {
 #pragma unroll
     for (int pq = 0; pq < 3; ++pq) {
       const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
