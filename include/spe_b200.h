@@ -137,6 +137,11 @@ size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypothese
  * scoring of the next batch on another stream; the refit then keeps its working matrix in local
  * instead of shared memory so that it fits next to the hypothesis kernel's CTAs. */
 #define SPE_FLAG_BACKGROUND_TAIL 4
+/* SPE_FLAG_JACOBI_SVD (scoring): take EPnP's four vectors from a full one-sided Jacobi SVD of M^T
+ * (the reference algorithm's eigensolve, 2.3x slower) instead of the default Householder QR + block
+ * inverse iteration.  Same results up to the chaos of near-degenerate hypotheses; kept for A/B
+ * measurements and for the test that compares the two (tests/test_pnp_gpu.py). */
+#define SPE_FLAG_JACOBI_SVD 8
 int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
                         float reproj_err, double confidence, float conf_floor, float* pose7,
                         uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,

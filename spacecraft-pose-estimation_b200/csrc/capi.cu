@@ -220,6 +220,10 @@ int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int
   a.confidence = confidence;
   a.conf_floor = conf_floor;
   a.adaptive = (flags & SPE_FLAG_ADAPTIVE) ? 1 : 0;
+  if ((flags & SPE_FLAG_JACOBI_SVD) && a.kernel_variant == 0) {
+    a.kernel_variant = 2;
+    a.jacobi_sweeps = 6;
+  }
   const cudaError_t e = spe::launch_ransac_score(model->m, a, ws, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }

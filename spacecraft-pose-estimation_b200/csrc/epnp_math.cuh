@@ -65,12 +65,14 @@ __device__ __forceinline__ void jacobi_angle(T a, T b, T p, T& c, T& s, T& t) {
   s = c * t;
 }
 
-// FP32: 4 MUFU + ~8 FP32 ops.  A rotation only has to be orthogonal to rounding accuracy, which
+// FP32: 3 MUFU + ~8 FP32 ops.  A rotation only has to be orthogonal to rounding accuracy, which
 // c = rsqrt(1 + t^2), s = c t guarantees irrespective of how exact t is.
 __device__ __forceinline__ void jacobi_angle_fast(float a, float b, float p, float& c, float& s, float& t) {
-  const float zeta = (b - a) * rcp_approx(p + p);
-  const float q = fabsf(zeta) + sqrt_approx(fmaf(zeta, zeta, 1.0f));  // zeta^2 = inf -> q = inf -> t = 0
-  t = copysignf(rcp_approx(q), zeta);
+  // t = 2p / (h + sign(h) sqrt(h^2 + 4p^2)), h = b - a  ==  sign(zeta) / (|zeta| + sqrt(zeta^2 + 1)) with zeta = h / 2p,
+  // in a 3-MUFU dependent chain (sqrt, rcp, rsqrt) instead of 4
+  const float h = b - a, gg = p + p;
+  const float q = sqrt_approx(fmaf(h, h, gg * gg));
+  t = gg * rcp_approx(h + copysignf(q, h));
   c = rsqrt_approx(fmaf(t, t, 1.0f));
   s = c * t;
 }
@@ -380,6 +382,93 @@ __device__ __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3])
     R[2][0] = -R[2][0];
     R[2][1] = -R[2][1];
     R[2][2] = -R[2][2];
+  }
+}
+
+// The same for NB independent matrices at once (FP32 hypothesis path: the three beta variants of one
+// hypothesis).  A single Procrustes is one long dependent chain (dot products -> 3 MUFU -> rotation,
+// 12 times); interleaving NB of them gives the scheduler NB independent chains per thread.
+template <int NB>
+__device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3], float (&R)[NB][3][3]) {
+  float B[NB][3][3], V[NB][3][3];
+#pragma unroll
+  for (int m = 0; m < NB; ++m)
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        B[m][i][j] = A[m][i][j];
+        V[m][i][j] = i == j ? 1.0f : 0.0f;
+      }
+#pragma unroll 1
+  for (int sweep = 0; sweep < Real<float>::svd3_sweeps; ++sweep) {
+#pragma unroll
+    for (int pq = 0; pq < 3; ++pq) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+      float c[NB], s[NB];
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        const float a = B[m][0][p] * B[m][0][p] + B[m][1][p] * B[m][1][p] + B[m][2][p] * B[m][2][p];
+        const float b = B[m][0][q] * B[m][0][q] + B[m][1][q] * B[m][1][q] + B[m][2][q] * B[m][2][q];
+        const float g = B[m][0][p] * B[m][0][q] + B[m][1][p] * B[m][1][q] + B[m][2][p] * B[m][2][q];
+        const bool rot = g * g > (Real<float>::eps * Real<float>::eps) * a * b;
+        float t;
+        jacobi_angle_fast(a, b, rot ? g : 1.0f, c[m], s[m], t);
+        c[m] = rot ? c[m] : 1.0f;
+        s[m] = rot ? s[m] : 0.0f;
+      }
+#pragma unroll
+      for (int m = 0; m < NB; ++m)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+          const float x = B[m][r][p], y = B[m][r][q];
+          B[m][r][p] = c[m] * x - s[m] * y;
+          B[m][r][q] = s[m] * x + c[m] * y;
+          const float vx = V[m][r][p], vy = V[m][r][q];
+          V[m][r][p] = c[m] * vx - s[m] * vy;
+          V[m][r][q] = s[m] * vx + c[m] * vy;
+        }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < NB; ++m) {
+    float n2[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) n2[j] = B[m][0][j] * B[m][0][j] + B[m][1][j] * B[m][1][j] + B[m][2][j] * B[m][2][j];
+    const int jmin = (n2[0] <= n2[1] && n2[0] <= n2[2]) ? 0 : (n2[1] <= n2[2] ? 1 : 2);
+    float U[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const float inv = rsqrt_approx(n2[j] > Real<float>::tiny ? n2[j] : 1.0f);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) U[r][j] = B[m][r][j] * inv;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j == jmin) {
+        const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        const float cx = U[1][j1] * U[2][j2] - U[2][j1] * U[1][j2];
+        const float cy = U[2][j1] * U[0][j2] - U[0][j1] * U[2][j2];
+        const float cz = U[0][j1] * U[1][j2] - U[1][j1] * U[0][j2];
+        const float along = cx * B[m][0][j] + cy * B[m][1][j] + cz * B[m][2][j];
+        const float sg = along < 0.0f ? -1.0f : 1.0f;
+        U[0][j] = sg * cx;
+        U[1][j] = sg * cy;
+        U[2][j] = sg * cz;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) R[m][r][cc] = U[r][0] * V[m][cc][0] + U[r][1] * V[m][cc][1] + U[r][2] * V[m][cc][2];
+    const float det = R[m][0][0] * (R[m][1][1] * R[m][2][2] - R[m][1][2] * R[m][2][1]) -
+                      R[m][0][1] * (R[m][1][0] * R[m][2][2] - R[m][1][2] * R[m][2][0]) +
+                      R[m][0][2] * (R[m][1][0] * R[m][2][1] - R[m][1][1] * R[m][2][0]);
+    if (det < 0.0f) {  // OpenCV's handling of a reflection: negate the third ROW of R (App. B.3j)
+      R[m][2][0] = -R[m][2][0];
+      R[m][2][1] = -R[m][2][1];
+      R[m][2][2] = -R[m][2][2];
+    }
   }
 }
 

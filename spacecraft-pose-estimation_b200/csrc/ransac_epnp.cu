@@ -1011,6 +1011,9 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
       }
 #pragma unroll
     for (int c = 0; c < 3; ++c) pw0[c] *= 0.2f;
+    // Gauss-Newton per variant (one after the other: it keeps L and its own 6x4 system live); the 3x3
+    // cross-covariances are parked so that the three Procrustes problems run interleaved afterwards.
+    float abt_all[3][3][3] = {}, pc0_all[3][3] = {};
 #pragma unroll 1
     for (int variant = 1; variant <= 3; ++variant) {
       float betas[4];
@@ -1048,26 +1051,41 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
         for (int r = 0; r < 3; ++r)
 #pragma unroll
           for (int c = 0; c < 3; ++c) abt[r][c] = fmaf(pcs[k][r] - pc0[r], pw[k][c] - pw0[c], abt[r][c]);
-      float R[3][3], t[3];
-      procrustes_uvt<float>(abt, R);
+      // static register indices only: select into the slot of this variant
 #pragma unroll
-      for (int r = 0; r < 3; ++r) t[r] = pc0[r] - (R[r][0] * pw0[0] + R[r][1] * pw0[1] + R[r][2] * pw0[2]);
+      for (int v = 0; v < 3; ++v) {
+        const bool mine = variant == v + 1;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) abt_all[v][r][c] = mine ? abt[r][c] : abt_all[v][r][c];
+          pc0_all[v][r] = mine ? pc0[r] : pc0_all[v][r];
+        }
+      }
+    }
+    float R_all[3][3][3];
+    procrustes_uvt_batch<3>(abt_all, R_all);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+      float t[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) t[r] = pc0_all[v][r] - (R_all[v][r][0] * pw0[0] + R_all[v][r][1] * pw0[1] + R_all[v][r][2] * pw0[2]);
       float sum = 0.f;
 #pragma unroll
       for (int k = 0; k < 5; ++k) {
-        const float Xc = R[0][0] * pw[k][0] + R[0][1] * pw[k][1] + R[0][2] * pw[k][2] + t[0];
-        const float Yc = R[1][0] * pw[k][0] + R[1][1] * pw[k][1] + R[1][2] * pw[k][2] + t[1];
-        const float iz = rcp_approx(R[2][0] * pw[k][0] + R[2][1] * pw[k][1] + R[2][2] * pw[k][2] + t[2]);
+        const float Xc = R_all[v][0][0] * pw[k][0] + R_all[v][0][1] * pw[k][1] + R_all[v][0][2] * pw[k][2] + t[0];
+        const float Yc = R_all[v][1][0] * pw[k][0] + R_all[v][1][1] * pw[k][1] + R_all[v][1][2] * pw[k][2] + t[1];
+        const float iz = rcp_approx(R_all[v][2][0] * pw[k][0] + R_all[v][2][1] * pw[k][1] + R_all[v][2][2] * pw[k][2] + t[2]);
         const float du = s_us[si[k]].x - (uc + fu * Xc * iz), dv = s_us[si[k]].y - (vc + fv * Yc * iz);
         sum += sqrt_approx(du * du + dv * dv);
       }
       const float err = sum * 0.2f;
-      if (variant == 1 || err < eb) {  // N = 1; if (e2 < e1) N = 2; if (e3 < e[N]) N = 3
+      if (v == 0 || err < eb) {  // N = 1; if (e2 < e1) N = 2; if (e3 < e[N]) N = 3
         eb = err;
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
 #pragma unroll
-          for (int c = 0; c < 3; ++c) Rb[r][c] = R[r][c];
+          for (int c = 0; c < 3; ++c) Rb[r][c] = R_all[v][r][c];
           tb[r] = t[r];
         }
       }

@@ -77,6 +77,7 @@ def _declare(L):
 FLAG_REFINE_LM = 1
 FLAG_ADAPTIVE = 2
 FLAG_BACKGROUND_TAIL = 4
+FLAG_JACOBI_SVD = 8
 
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",

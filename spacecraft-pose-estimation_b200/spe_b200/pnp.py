@@ -104,14 +104,17 @@ class PnPSolver:
     # -- the batched solve
     def solve_device(self, kpts, hypotheses: int = 256, reproj_err: float = 15.0, confidence: float = 0.99,
                      conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, want_rt: bool = True, refine: str | None = None,
-                     adaptive: bool = False) -> PoseBatch:
+                     adaptive: bool = False, eig: str = "qr") -> PoseBatch:
         """kpts [B,J,3] float32 CUDA contiguous -> PoseBatch of CUDA tensors.  Enqueues on torch's
-        current stream and does not synchronise.  refine="lm" adds a reprojection-error
+        current stream and does not synchronise.  eig="jacobi" scores the hypotheses with the full
+        Jacobi SVD of M^T instead of the default QR + inverse iteration (A/B and tests).  refine="lm" adds a reprojection-error
         Levenberg-Marquardt step on the inliers (cv2.solvePnPRefineLM's result); the reference does
         not do that, so it is off by default."""
         torch = _lib.require_cuda()
         if refine not in (None, "lm"):
             raise ValueError("refine must be None or 'lm'")
+        if eig not in ("qr", "jacobi"):
+            raise ValueError("eig must be 'qr' or 'jacobi'")
         assert kpts.is_cuda and kpts.dtype == torch.float32 and kpts.is_contiguous()
         B, J, three = kpts.shape
         if J != self.J or three != 3:
@@ -131,7 +134,8 @@ class PnPSolver:
                                                    float(confidence), float(conf_floor), pose7.data_ptr(), mask.data_ptr(),
                                                    status.data_ptr(), winner.data_ptr(), rt.data_ptr() if want_rt else None,
                                                    ws.data_ptr(), ws.numel(),
-                                                   (_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0), stream),
+                                                   (_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0) |
+                                                   (_lib.FLAG_JACOBI_SVD if eig == "jacobi" else 0), stream),
                        "spe_ransac_epnp_f32")
         return PoseBatch(pose7, mask, status, winner, rt)
 
