@@ -9,6 +9,10 @@ namespace spe {
 
 constexpr int kMaxLandmarks = 32;
 constexpr int kModelPoints = 5;  // EPnP minimal set used by cv2.solvePnPRansac
+// one control-point table entry: alpha[5][3] (points in ascending landmark order; alpha_k0 = 1 - sum),
+// k_i^2 [3] (squared control-point distances from the centroid: they give rho), pad[2].  The control
+// points themselves are not needed by the hypothesis kernel.
+constexpr int kCtrlEntryFloats = 20;
 
 struct Camera {
   double fx, fy, cx, cy;
@@ -25,6 +29,11 @@ struct Model {
   float* d_landmarks = nullptr;                 // [J,3] float32
   uint8_t* d_subsets = nullptr;                 // [J-5][max_hyp][5]: minimal sets for n = 6..J
   std::vector<uint8_t> h_subsets;               // host copy of the same table
+  // Control points / barycentric coordinates of EVERY 5-subset of the J landmarks (they depend on the
+  // object points only): C(J,5) entries of kCtrlEntryFloats floats, indexed by the combinatorial rank
+  // of the sorted landmark ids (ransac_epnp.cu: build_control_table / hypothesis_kernel_t1).
+  float* d_ctrl = nullptr;
+  size_t ctrl_entries = 0;
 };
 
 // Workspace carve-up for B frames x H hypotheses (all offsets 16-byte aligned).

@@ -62,6 +62,78 @@ void opencv_minimal_sets(int count, int num, uint8_t* out) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Control points of every 5-subset (host, float64, once per model).  EPnP's control points are the
+// centroid and the PCA axes of the object points scaled by sqrt(lambda_i / 5) (App. B.3c), the
+// barycentric coordinates alpha_ki = (p_k - c0) . v_i / k_i; both depend on the 5 landmarks only, so
+// the hypothesis kernel looks them up instead of running a 5x3 Jacobi per hypothesis.  Entry order =
+// combinatorial number system: rank(j0<j1<j2<j3<j4) = C(j0,1)+C(j1,2)+C(j2,3)+C(j3,4)+C(j4,5).
+static void sym3_jacobi(double S[3][3], double V[3][3]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    const double off = fabs(S[0][1]) + fabs(S[0][2]) + fabs(S[1][2]);
+    if (off <= 1e-300 || off <= 1e-18 * (fabs(S[0][0]) + fabs(S[1][1]) + fabs(S[2][2]))) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (S[p][q] == 0.0) continue;
+        const double zeta = (S[q][q] - S[p][p]) / (2.0 * S[p][q]);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), sn = c * t;
+        for (int k = 0; k < 3; ++k) {  // S <- S J
+          const double x = S[k][p], y = S[k][q];
+          S[k][p] = c * x - sn * y, S[k][q] = sn * x + c * y;
+        }
+        for (int k = 0; k < 3; ++k) {  // S <- J^T S
+          const double x = S[p][k], y = S[q][k];
+          S[p][k] = c * x - sn * y, S[q][k] = sn * x + c * y;
+        }
+        for (int k = 0; k < 3; ++k) {
+          const double x = V[k][p], y = V[k][q];
+          V[k][p] = c * x - sn * y, V[k][q] = sn * x + c * y;
+        }
+      }
+  }
+}
+
+static void build_control_table(const Model& m, std::vector<float>& table) {
+  const int J = m.J;
+  size_t count = 0;
+  for (int a = 4; a < J; ++a) count += (size_t)a * (a - 1) * (a - 2) * (a - 3) / 24;  // C(J,5) = sum C(a,4)
+  table.assign(count * kCtrlEntryFloats, 0.f);
+  size_t rank = 0;  // j4 outermost ... j0 innermost enumerates the ranks in increasing order
+  for (int j4 = 4; j4 < J; ++j4)
+    for (int j3 = 3; j3 < j4; ++j3)
+      for (int j2 = 2; j2 < j3; ++j2)
+        for (int j1 = 1; j1 < j2; ++j1)
+          for (int j0 = 0; j0 < j1; ++j0, ++rank) {
+            const int ids[5] = {j0, j1, j2, j3, j4};
+            double P[5][3], c0[3] = {0, 0, 0};
+            for (int k = 0; k < 5; ++k)
+              for (int c = 0; c < 3; ++c) {
+                P[k][c] = (double)m.landmarks_f32[3 * ids[k] + c];
+                c0[c] += P[k][c] * 0.2;
+              }
+            double S[3][3] = {}, V[3][3];
+            for (int k = 0; k < 5; ++k)
+              for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) S[r][c] += (P[k][r] - c0[r]) * (P[k][c] - c0[c]);
+            sym3_jacobi(S, V);
+            float* e = table.data() + rank * kCtrlEntryFloats;
+            for (int i = 0; i < 3; ++i) {
+              const double lam = S[i][i] > 0.0 ? S[i][i] : 0.0;
+              const double ki = sqrt(lam * 0.2);
+              const double inv = ki > 1e-12 ? 1.0 / ki : 0.0;
+              for (int k = 0; k < 5; ++k) {
+                double proj = 0.0;
+                for (int c = 0; c < 3; ++c) proj += (P[k][c] - c0[c]) * V[c][i];
+                e[3 * k + i] = (float)(proj * inv);
+              }
+              e[15 + i] = (float)(ki * ki);
+            }
+          }
+}
+
 cudaError_t model_upload(Model& m) {
   cudaError_t e = cudaGetDevice(&m.device);
   if (e != cudaSuccess) return e;
@@ -76,6 +148,13 @@ cudaError_t model_upload(Model& m) {
     e = cudaMalloc(&m.d_subsets, m.h_subsets.size());
     if (e != cudaSuccess) return e;
     e = cudaMemcpy(m.d_subsets, m.h_subsets.data(), m.h_subsets.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return e;
+    std::vector<float> ctrl;
+    build_control_table(m, ctrl);
+    m.ctrl_entries = ctrl.size() / kCtrlEntryFloats;
+    e = cudaMalloc(&m.d_ctrl, ctrl.size() * sizeof(float));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpy(m.d_ctrl, ctrl.data(), ctrl.size() * sizeof(float), cudaMemcpyHostToDevice);
   }
   return e;
 }
@@ -83,8 +162,10 @@ cudaError_t model_upload(Model& m) {
 void model_free(Model& m) {
   if (m.d_landmarks) cudaFree(m.d_landmarks);
   if (m.d_subsets) cudaFree(m.d_subsets);
+  if (m.d_ctrl) cudaFree(m.d_ctrl);
   m.d_landmarks = nullptr;
   m.d_subsets = nullptr;
+  m.d_ctrl = nullptr;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -122,6 +203,7 @@ struct DevModel {
   const uint8_t* subsets;  // [J-5][max_hyp][5]
   int J, max_hyp;
   Camera cam;
+  const float4* ctrl;  // [C(J,5)][kCtrlEntryFloats / 4] control-point table (thread-per-hypothesis kernel)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -543,11 +625,11 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
 #ifndef SPE_REFIT_REGS
 #define SPE_REFIT_REGS 255
 #endif
-constexpr int kT1Threads = 128;
 __device__ __forceinline__ int ws_frames(const RansacWorkspace& ws) { return ws.frames; }
 constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alphas[5][4] (+1: odd stride, conflict-free)
 // shared memory of one warp: landmarks [32][3], ideal + raw pixels [32] float2 each, per-thread scratch
-constexpr int kT1WarpBytes = (int)(sizeof(float) * 3 * kMaxLandmarks + 2 * sizeof(float2) * kMaxLandmarks + sizeof(float) * 32 * kT1Stride);
+constexpr int kT1WarpBytes = (int)(sizeof(float) * 3 * kMaxLandmarks + 2 * sizeof(float2) * kMaxLandmarks + sizeof(float) * 32 * kT1Stride +
+                                   kMaxLandmarks /* landmark id of every compacted point */);
 static_assert(kT1WarpBytes % 16 == 0, "per-warp shared-memory slice must stay 16-byte aligned");
 
 // One Jacobi rotation between the columns at register positions P and Q of A, with the two
@@ -837,6 +919,7 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
   float2* s_us = reinterpret_cast<float2*>(wbase + sizeof(float) * 3 * kMaxLandmarks);
   float2* s_img = s_us + kMaxLandmarks;
   float* work = reinterpret_cast<float*>(s_img + kMaxLandmarks) + lane * kT1Stride;
+  uint8_t* s_id = reinterpret_cast<uint8_t*>(reinterpret_cast<float*>(s_img + kMaxLandmarks) + 32 * kT1Stride);
   const long long item = (long long)blockIdx.x * kWarps + warp;
   const int b = (int)(item / hblocks), hb = (int)(item - (long long)b * hblocks);
   if (b >= ws_frames(ws)) return;
@@ -853,24 +936,59 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
     s_us[lane] = ws.us_hyp[(size_t)b * m.J + j];
     const float* k = kpts + ((size_t)b * m.J + j) * 3;
     s_img[lane] = make_float2(k[0], k[1]);
+    s_id[lane] = (uint8_t)j;
   }
   __syncwarp();
   if (h >= H) return;
   const uint8_t* sub = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
+  // The five points are handled in ascending landmark order (EPnP does not depend on the order of
+  // its points beyond rounding): that is the order of the control-point table's alphas.  Key =
+  // landmark id * 32 + compacted index, sorted with a 9-exchange network.
   int si[5];
+  unsigned ctrl_rank;
+  {
+    int key[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) si[k] = sub[k];
+    for (int k = 0; k < 5; ++k) {
+      const int idx = sub[k];
+      key[k] = ((int)s_id[idx] << 5) | idx;
+    }
+    auto cx = [&](int a, int b) {
+      const int lo = min(key[a], key[b]), hi = max(key[a], key[b]);
+      key[a] = lo, key[b] = hi;
+    };
+    cx(0, 1), cx(3, 4), cx(2, 4), cx(2, 3), cx(0, 3), cx(0, 2), cx(1, 4), cx(1, 3), cx(1, 2);
+    unsigned j[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) si[k] = key[k] & 31, j[k] = (unsigned)key[k] >> 5;
+    // C(j0,1) + C(j1,2) + C(j2,3) + C(j3,4) + C(j4,5); every product is exactly divisible
+    ctrl_rank = j[0] + j[1] * (j[1] - 1) / 2 + j[2] * (j[2] - 1) * (j[2] - 2) / 6 + j[3] * (j[3] - 1) * (j[3] - 2) * (j[3] - 3) / 24 +
+                j[4] * (j[4] - 1) * (j[4] - 2) * (j[4] - 3) / 24 * (j[4] - 4) / 5;
+  }
   const float fu = (float)m.cam.fx, fv = (float)m.cam.fy, uc = (float)m.cam.cx, vc = (float)m.cam.cy;
 
   // ---- control points, alphas, M^T ---------------------------------------------------------
   float rho[6];
   float A[12][10], d[10];
   {
-    float pw[5][3], al[5][4], cws[4][3];
+    float al[5][4];
+    {
+      float e[kCtrlEntryFloats];
+      const float4* src = m.ctrl + (size_t)ctrl_rank * (kCtrlEntryFloats / 4);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) pw[k][0] = s_pw[si[k]][0], pw[k][1] = s_pw[si[k]][1], pw[k][2] = s_pw[si[k]][2];
-    control_points5(pw, cws, al);
-    build_rho<float>(cws, rho);
+      for (int q = 0; q < kCtrlEntryFloats / 4; ++q) {
+        const float4 v = __ldg(src + q);
+        e[4 * q] = v.x, e[4 * q + 1] = v.y, e[4 * q + 2] = v.z, e[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        al[k][1] = e[3 * k], al[k][2] = e[3 * k + 1], al[k][3] = e[3 * k + 2];
+        al[k][0] = 1.0f - al[k][1] - al[k][2] - al[k][3];
+      }
+      // rho over the control-point pairs (0,1)(0,2)(0,3)(1,2)(1,3)(2,3): the axes are orthogonal
+      rho[0] = e[15], rho[1] = e[16], rho[2] = e[17];
+      rho[3] = e[15] + e[16], rho[4] = e[15] + e[17], rho[5] = e[16] + e[17];
+    }
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       const float du = uc - s_us[si[k]].x, dv = vc - s_us[si[k]].y;
@@ -1836,7 +1954,7 @@ __global__ void debug_scores_kernel(RansacWorkspace ws, long long total, int32_t
 
 cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
-  DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam};
+  DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam, reinterpret_cast<const float4*>(m.d_ctrl)};
   const int wpb = 4;
   frame_prep_kernel<<<(a.B + wpb - 1) / wpb, wpb * 32, 0, stream>>>(dm, a.kpts, a.B, a.conf_floor, ws);
   cudaError_t e = cudaGetLastError();
@@ -1889,7 +2007,7 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
 
 cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
   if (a.B == 0) return cudaSuccess;
-  DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam};
+  DevModel dm{m.d_landmarks, m.d_subsets, m.J, m.max_hyp, m.cam, reinterpret_cast<const float4*>(m.d_ctrl)};
   // Without a common carveout the kernel flips idle SMs to an all-L1 split and the next batch's
   // decode CTAs must wait for it to finish: measured 0.12 -> 0.32 ms decode when overlapped.
   static PerDeviceOnce once;
