@@ -187,6 +187,15 @@ static int t1_warps_setting() {
   return warps;
 }
 
+static int tail_warps_setting() {
+  static int warps = [] {
+    const char* v = getenv("SPE_TAIL_WARPS");  // dev knob: warps per CTA of the background select/refit kernel
+    const int w = v ? atoi(v) : 8;
+    return w >= 1 && w <= 8 ? w : 8;
+  }();
+  return warps;
+}
+
 static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, void* workspace, size_t workspace_bytes, spe::RansacArgs& a,
                             spe::RansacWorkspace& ws) {
   if (model == nullptr || B < 0 || hypotheses < 1 || hypotheses > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
@@ -204,6 +213,7 @@ static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, voi
   a.jacobi_sweeps = jacobi_sweeps_setting();
   a.kernel_variant = hyp_kernel_setting();
   a.t1_warps = t1_warps_setting();
+  a.tail_warps = tail_warps_setting();
   ws = spe::carve_workspace(workspace, model->m.J, B, hypotheses);
   return SPE_OK;
 }

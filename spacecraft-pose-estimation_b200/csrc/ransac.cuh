@@ -63,6 +63,7 @@ struct RansacArgs {
   int refine_lm;              // SPE_FLAG_REFINE_LM
   int adaptive;               // SPE_FLAG_ADAPTIVE: score only the hypotheses cv2 could look at
   int refit_background;       // the tail runs under other kernels: keep its shared-memory footprint at zero
+  int tail_warps;             // warps per CTA of the background select/refit kernel (1..8)
   int t1_warps;               // warps per CTA of the thread-per-hypothesis kernel (1..4)
   int kernel_variant;  // 0: thread per hypothesis, QR + inverse iteration (default); 1: 4 lanes per hypothesis; 2: thread per hypothesis, Jacobi SVD
   float* pose7;           // [B,7]

@@ -2019,7 +2019,12 @@ cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, cons
   if (ce != cudaSuccess) return ce;
   const int ctas = (a.B + 7) / 8;  // 4 lanes per frame, one warp per CTA
   if (a.refit_background) {
-    select_refit_kernel<false><<<ctas, 32, 0, stream>>>(dm, a, ws);
+    // Background tail: the warps are packed `tail_warps` to a CTA (8 x 255 registers = a whole SM) so that
+    // they hide each other's latency on FEW SMs instead of each blocking a 21 K-register CTA slot of the
+    // next batch's hypothesis kernel on EVERY SM (profiles/step_r1.md, tools/overlap_probe.py).
+    const int warps = a.tail_warps >= 1 && a.tail_warps <= 8 ? a.tail_warps : 8;
+    const int threads = 32 * warps;
+    select_refit_kernel<false><<<(a.B * 4 + threads - 1) / threads, threads, 0, stream>>>(dm, a, ws);
   } else {
     select_refit_kernel<true><<<ctas, 32, sizeof(double) * 144 * 32, stream>>>(dm, a, ws);
   }

@@ -208,7 +208,7 @@ class StreamedHeatmapToPose:
         dev, J, H = stage.device, stage.solver.J, stage.hypotheses
         self._L = stage._L
         self.main = torch.cuda.current_stream(dev)
-        self.side = torch.cuda.Stream(dev)
+        self.side = torch.cuda.Stream(dev)  # (a high-priority side stream changes nothing: measured)
         self.ws_bytes = int(self._L.spe_ransac_workspace_bytes(stage.solver.handle, self.B, H))
         self.slots = []
         for _ in range(self.depth):
