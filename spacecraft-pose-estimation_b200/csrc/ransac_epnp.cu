@@ -756,14 +756,23 @@ __device__ __forceinline__ void jacobi_mt(float (&A)[12][10], float (&d)[10], in
 // NumPy model tools/proto_eig.py before it was written and on the GPU afterwards: per-hypothesis
 // inlier-count agreement and winner-mask agreement are the same as with the Jacobi SVD.
 // ~3.7 k instead of ~18 k instructions per hypothesis for this stage.
+// Row/column order of A = M^T in this routine (eig_row / the fill in the kernel): columns 0..4 are the
+// x-equations of the five points, 5..9 their y-equations; rows 0..7 are the (x, z) components of the
+// four control points, rows 8..11 the y components.  An x-equation has no y component, so the first
+// five reflectors and the columns they come from live in rows 0..7 only: every inner loop of steps
+// 0..4 (and of their later applications) stops at row 8 instead of 12 (kQrRowEnd).
+__device__ __forceinline__ constexpr int kQrRowEnd(int k) { return k < 5 ? 8 : 12; }
+// position in the 12-vector (control point j, component c) <- row of A
+__device__ __forceinline__ constexpr int eig_row_to_coord(int r) { return r < 8 ? 3 * (r / 2) + ((r & 1) ? 2 : 0) : 3 * (r - 8) + 1; }
+
 __device__ __forceinline__ void eig_qr_inverse_iteration(float (&A)[12][10], float* __restrict__ work, int iters) {
-  // ---- Householder QR, H_k = I - tau_k v_k v_k^T with v_k = (1, A[k+1..11][k]) -----------------
+  // ---- Householder QR, H_k = I - tau_k v_k v_k^T with v_k = (1, A[k+1..][k]) --------------------
   // tau_k is parked in work[24 + k] (the v2 slot is free until the very end).
 #pragma unroll
   for (int k = 0; k < 10; ++k) {
     float ss = 0.f;
 #pragma unroll
-    for (int i = k + 1; i < 12; ++i) ss = fmaf(A[i][k], A[i][k], ss);
+    for (int i = k + 1; i < kQrRowEnd(k); ++i) ss = fmaf(A[i][k], A[i][k], ss);
     const float x0 = A[k][k];
     const float nn = fmaf(x0, x0, ss);
     const bool ok = nn > 1e-30f;
@@ -774,16 +783,16 @@ __device__ __forceinline__ void eig_qr_inverse_iteration(float (&A)[12][10], flo
     work[24 + k] = tau;
     A[k][k] = -copysignf(nrm, x0);
 #pragma unroll
-    for (int i = k + 1; i < 12; ++i) A[i][k] *= iv0;
+    for (int i = k + 1; i < kQrRowEnd(k); ++i) A[i][k] *= iv0;
 #pragma unroll
     for (int j = k + 1; j < 10; ++j) {
       float s = A[k][j];
 #pragma unroll
-      for (int i = k + 1; i < 12; ++i) s = fmaf(A[i][k], A[i][j], s);
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) s = fmaf(A[i][k], A[i][j], s);
       s *= tau;
       A[k][j] -= s;
 #pragma unroll
-      for (int i = k + 1; i < 12; ++i) A[i][j] = fmaf(-s, A[i][k], A[i][j]);
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) A[i][j] = fmaf(-s, A[i][k], A[i][j]);
     }
   }
   // y <- Q y = H_0 ( ... (H_9 y))
@@ -792,11 +801,11 @@ __device__ __forceinline__ void eig_qr_inverse_iteration(float (&A)[12][10], flo
     for (int k = 9; k >= 0; --k) {
       float s = y[k];
 #pragma unroll
-      for (int i = k + 1; i < 12; ++i) s = fmaf(A[i][k], y[i], s);
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) s = fmaf(A[i][k], y[i], s);
       s *= work[24 + k];
       y[k] -= s;
 #pragma unroll
-      for (int i = k + 1; i < 12; ++i) y[i] = fmaf(-s, A[i][k], y[i]);
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) y[i] = fmaf(-s, A[i][k], y[i]);
     }
   };
   // ---- null space: the last two columns of Q ---------------------------------------------------
@@ -807,7 +816,7 @@ __device__ __forceinline__ void eig_qr_inverse_iteration(float (&A)[12][10], flo
     for (int r = 0; r < 12; ++r) y[r] = r == 10 + c ? 1.0f : 0.0f;
     apply_q(y);
 #pragma unroll
-    for (int r = 0; r < 12; ++r) work[12 * c + r] = y[r];
+    for (int r = 0; r < 12; ++r) work[12 * c + eig_row_to_coord(r)] = y[r];
   }
   // ---- block inverse iteration on R R^T ---------------------------------------------------------
   float rinv[10];
@@ -899,7 +908,7 @@ __device__ __forceinline__ void eig_qr_inverse_iteration(float (&A)[12][10], flo
     apply_q(y2);
     apply_q(y3);
 #pragma unroll
-    for (int r = 0; r < 12; ++r) work[24 + r] = y2[r], work[36 + r] = y3[r];
+    for (int r = 0; r < 12; ++r) work[24 + eig_row_to_coord(r)] = y2[r], work[36 + eig_row_to_coord(r)] = y3[r];
   }
 }
 
@@ -996,8 +1005,13 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
       for (int j = 0; j < 4; ++j) {
         const float a = al[k][j];
         work[48 + 4 * k + j] = a;
-        A[3 * j][2 * k] = a * fu, A[3 * j + 1][2 * k] = 0.f, A[3 * j + 2][2 * k] = a * du;
-        A[3 * j][2 * k + 1] = 0.f, A[3 * j + 1][2 * k + 1] = a * fv, A[3 * j + 2][2 * k + 1] = a * dv;
+        if constexpr (kEig == 0) {  // rows (x, z) of control point j, then the y rows; x-equations first
+          A[2 * j][k] = a * fu, A[2 * j + 1][k] = a * du, A[8 + j][k] = 0.f;
+          A[2 * j][5 + k] = 0.f, A[2 * j + 1][5 + k] = a * dv, A[8 + j][5 + k] = a * fv;
+        } else {
+          A[3 * j][2 * k] = a * fu, A[3 * j + 1][2 * k] = 0.f, A[3 * j + 2][2 * k] = a * du;
+          A[3 * j][2 * k + 1] = 0.f, A[3 * j + 1][2 * k + 1] = a * fv, A[3 * j + 2][2 * k + 1] = a * dv;
+        }
       }
     }
   }
