@@ -190,8 +190,8 @@ static int t1_warps_setting() {
 static int tail_warps_setting() {
   static int warps = [] {
     const char* v = getenv("SPE_TAIL_WARPS");  // dev knob: warps per CTA of the background select/refit kernel
-    const int w = v ? atoi(v) : 8;
-    return w >= 1 && w <= 8 ? w : 8;
+    const int w = v ? atoi(v) : 0;  // 0: as many as fit one SM
+    return w >= 1 && w <= 32 ? w : 0;
   }();
   return warps;
 }

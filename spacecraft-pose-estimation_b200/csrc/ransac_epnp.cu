@@ -1379,6 +1379,27 @@ struct LocalMat12 {  // the same matrix in the thread's local memory (small foot
   double (*a)[12];
   __device__ __forceinline__ double& operator()(int r, int c) const { return a[r][c]; }
 };
+// ONE copy per frame in shared memory, used by all four lanes of the frame's group.  After the
+// accumulation every lane would hold the same matrix and the tridiagonalisation / QL steps are the same
+// instructions on the same data in lockstep, so the lanes read the same address (a broadcast) and
+// write the same value.  9.3 KB per warp instead of 36.9 KB (per-thread copies in shared memory) or
+// 36.9 KB of local memory streaming through L1: eight such warps fit one SM.  The frame stride of
+// 145 doubles keeps the eight frames of a warp on different banks.
+constexpr int kFrameMatStride = 145;
+struct FrameMat12 {
+  static constexpr bool kSharedPerFrame = true;
+  double* base;  // &storage[frame slot * kFrameMatStride]
+  __device__ __forceinline__ double& operator()(int r, int c) const { return base[r * 12 + c]; }
+};
+template <typename Mat>
+struct MatTraits {
+  static constexpr bool kSharedPerFrame = false;
+};
+template <>
+struct MatTraits<FrameMat12> {
+  static constexpr bool kSharedPerFrame = true;
+};
+
 
 // Called by the 4 lanes of a frame's group with identical inputs (sub = lane within the group,
 // gmask = the group's lanes): the reduction and the eigenvalues are computed redundantly, then lane
@@ -1660,6 +1681,42 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
     for (int j = 0; j < 3; ++j) al[i][1 + j] = (cov[3 * j] * q[0] + cov[3 * j + 1] * q[1] + cov[3 * j + 2] * q[2]) * inv_k[j];
     al[i][0] = 1.0 - al[i][1] - al[i][2] - al[i][3];
   }
+  if constexpr (MatTraits<Mat>::kSharedPerFrame) {
+    // MtM (12x12), one copy per frame.  Row 2i of M = alpha_i (x) (fu, 0, du_i), row 2i+1 = alpha_i (x) (0, fv, dv_i)
+    // with du_i = uc - u_i, dv_i = vc - v_i, so every entry is fu^2, fv^2, fu, fv or 1 times one of the 40 sums
+    //   S_m[jr][jc] = sum_i alpha_i[jr] alpha_i[jc] w_m(i),  w = 1, du_i, dv_i, du_i^2 + dv_i^2,  jr <= jc.
+    // Lane `sub` computes the sums t = sub, sub + 4, ... and scatters them (with their transposes).
+    for (int idx = sub; idx < 144; idx += 4) mtm(idx / 12, idx - 12 * (idx / 12)) = 0.0;  // (x, y) cross entries stay 0
+    __syncwarp(gmask);
+    for (int t = sub; t < 40; t += 4) {
+      const int mi = t / 10, pr = t - 10 * mi;  // pairs (0,0)(0,1)(0,2)(0,3)(1,1)(1,2)(1,3)(2,2)(2,3)(3,3)
+      const int jr = pr < 4 ? 0 : (pr < 7 ? 1 : (pr < 9 ? 2 : 3));
+      const int jc = pr < 4 ? pr : (pr < 7 ? pr - 3 : (pr < 9 ? pr - 5 : 3));
+      double acc = 0.0;
+      for (int i = 0; i < n; ++i) {
+        const double du = uc - us[i][0], dv = vc - us[i][1];
+        const double w = mi == 0 ? 1.0 : (mi == 1 ? du : (mi == 2 ? dv : du * du + dv * dv));
+        acc += al[i][jr] * al[i][jc] * w;
+      }
+      auto set = [&](int r, int c, double v) {
+        mtm(r, c) = v;
+        mtm(c, r) = v;
+      };
+      if (mi == 0) {
+        set(3 * jr, 3 * jc, fu * fu * acc);
+        set(3 * jr + 1, 3 * jc + 1, fv * fv * acc);
+      } else if (mi == 1) {
+        set(3 * jr, 3 * jc + 2, fu * acc);
+        set(3 * jr + 2, 3 * jc, fu * acc);
+      } else if (mi == 2) {
+        set(3 * jr + 1, 3 * jc + 2, fv * acc);
+        set(3 * jr + 2, 3 * jc + 1, fv * acc);
+      } else {
+        set(3 * jr + 2, 3 * jc + 2, acc);
+      }
+    }
+    __syncwarp(gmask);
+  } else {
   // MtM (12x12): upper triangle over this lane's points, summed over the group, mirrored
   for (int r = 0; r < 12; ++r)
     for (int c = 0; c < 12; ++c) mtm(r, c) = 0.0;
@@ -1681,6 +1738,7 @@ __device__ void epnp_f64(int n, const double (*pw)[3], const double (*und)[2], c
       mtm(r, c) = x;
       mtm(c, r) = x;
     }
+  }
   // eigenvectors of MtM for the four smallest eigenvalues: v0 = smallest (OpenCV's ut[11]) ... v3
   double v[4][12];
   sym_eig_smallest4<12, Mat>(mtm, v, sub, gmask);
@@ -1883,7 +1941,9 @@ __device__ void refine_lm_f64(int n, const double (*pw)[3], const double (*img)[
 // when the kernel has the GPU to itself) or in local memory (no shared-memory footprint: the
 // variant used when it runs as a background tail under the next batch's hypothesis kernel, whose
 // three CTAs per SM leave no room for 36 KB more).
-template <bool kSmemMat>
+// kMatMode 2: one shared-memory copy per frame (FrameMat12, 9.3 KB per warp): what both launch shapes use now;
+// 0 and 1 stay selectable with SPE_REFIT_MAT for A/B measurements.
+template <int kMatMode>
 __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, RansacArgs a, RansacWorkspace ws) {
   const int lane = threadIdx.x & 31, sub = lane & 3;
   const unsigned gmask = 0xFu << (lane & ~3);
@@ -1931,7 +1991,10 @@ __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, Rans
         und[k][1] = n == kModelPoints ? (double)(float)q.y : q.y;
         ++k;
       }
-    if constexpr (kSmemMat) {
+    if constexpr (kMatMode == 2) {
+      extern __shared__ double s_mat[];  // [blockDim.x / 4][kFrameMatStride]
+      epnp_f64(k, pw, und, m.cam, R, t, sub, gmask, FrameMat12{s_mat + (threadIdx.x >> 2) * kFrameMatStride});
+    } else if constexpr (kMatMode == 1) {
       extern __shared__ double s_mat[];  // [144][blockDim.x]
       epnp_f64(k, pw, und, m.cam, R, t, sub, gmask, SmemMat12{s_mat + threadIdx.x, (int)blockDim.x});
     } else {
@@ -2026,21 +2089,31 @@ cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, cons
   // decode CTAs must wait for it to finish: measured 0.12 -> 0.32 ms decode when overlapped.
   static PerDeviceOnce once;
   const cudaError_t ce = once.run(m.device, [] {
-    cudaError_t r = cudaFuncSetAttribute(select_refit_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
-    if (r == cudaSuccess) r = cudaFuncSetAttribute(select_refit_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    cudaError_t r = cudaFuncSetAttribute(select_refit_kernel<0>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(select_refit_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(select_refit_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(select_refit_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 8 * kFrameMatStride * (int)sizeof(double));
     return r;
   });
   if (ce != cudaSuccess) return ce;
-  const int ctas = (a.B + 7) / 8;  // 4 lanes per frame, one warp per CTA
-  if (a.refit_background) {
-    // Background tail: the warps are packed `tail_warps` to a CTA (8 x 255 registers = a whole SM) so that
-    // they hide each other's latency on FEW SMs instead of each blocking a 21 K-register CTA slot of the
-    // next batch's hypothesis kernel on EVERY SM (profiles/step_r1.md, tools/overlap_probe.py).
-    const int warps = a.tail_warps >= 1 && a.tail_warps <= 8 ? a.tail_warps : 8;
-    const int threads = 32 * warps;
-    select_refit_kernel<false><<<(a.B * 4 + threads - 1) / threads, threads, 0, stream>>>(dm, a, ws);
+  // 4 lanes per frame.  Background tail: the warps are packed 8 to a CTA (8 x 255 registers = a whole SM) so that
+  // they hide each other's latency on FEW SMs instead of each blocking a 21 K-register CTA slot of the next
+  // batch's hypothesis kernel on EVERY SM (profiles/step_r1.md, tools/overlap_probe.py).  Alone: one warp per CTA.
+  constexpr int kMaxTailWarps = 65536 / (32 * ((SPE_REFIT_REGS + 7) / 8 * 8));  // one CTA = the register file of one SM
+  int warps = a.refit_background ? kMaxTailWarps : 1;
+  if (a.tail_warps >= 1 && a.tail_warps <= kMaxTailWarps) warps = a.tail_warps;
+  const int threads = 32 * warps;
+  const int ctas = (a.B * 4 + threads - 1) / threads;
+  static const int mat_mode = [] {
+    const char* v = getenv("SPE_REFIT_MAT");  // dev knob: 0 local memory, 1 per-thread shared copies, 2 per-frame shared copy
+    return v ? atoi(v) : 2;
+  }();
+  if (mat_mode == 0 || (mat_mode == 1 && warps > 1)) {
+    select_refit_kernel<0><<<ctas, threads, 0, stream>>>(dm, a, ws);
+  } else if (mat_mode == 1) {
+    select_refit_kernel<1><<<ctas, 32, sizeof(double) * 144 * 32, stream>>>(dm, a, ws);
   } else {
-    select_refit_kernel<true><<<ctas, 32, sizeof(double) * 144 * 32, stream>>>(dm, a, ws);
+    select_refit_kernel<2><<<ctas, threads, sizeof(double) * kFrameMatStride * 8 * warps, stream>>>(dm, a, ws);
   }
   return cudaGetLastError();
 }
