@@ -1409,6 +1409,13 @@ template <int N, typename Mat>
 __device__ void sym_eig_smallest4(Mat V, double (&out)[4][N], int sub, unsigned gmask) {
   const int gbase = (threadIdx.x & 31) & ~3;
   double d[N], e[N], hs[N], diag[N];
+  // A matrix shared by the four lanes of the group (FrameMat12): the lanes hold d, e replicated in registers and
+  // read the matrix; lane 0 writes it, except in the rank-2 update where the lanes split the rows of a column.
+  // Every write is separated from the other lanes' reads of the same entry by a __syncwarp of the group: once per
+  // outer step, and once per column of the rank-2 update (every lane needs V(i-1, j) back, which it computes
+  // itself from the value read before the barrier).
+  constexpr bool kShared = MatTraits<Mat>::kSharedPerFrame;
+  const bool writer = !kShared || sub == 0;
   // --- reduction to tridiagonal form
   for (int j = 0; j < N; ++j) d[j] = V(N - 1, j);
   for (int i = N - 1; i > 0; --i) {
@@ -1418,8 +1425,10 @@ __device__ void sym_eig_smallest4(Mat V, double (&out)[4][N], int sub, unsigned 
       e[i] = d[i - 1];
       for (int j = 0; j < i; ++j) {
         d[j] = V(i - 1, j);
-        V(i, j) = 0.0;
-        V(j, i) = 0.0;
+        if (writer) {
+          V(i, j) = 0.0;
+          V(j, i) = 0.0;
+        }
       }
     } else {
       const double inv_scale = 1.0 / scale;
@@ -1436,7 +1445,7 @@ __device__ void sym_eig_smallest4(Mat V, double (&out)[4][N], int sub, unsigned 
       for (int j = 0; j < i; ++j) e[j] = 0.0;
       for (int j = 0; j < i; ++j) {
         f = d[j];
-        V(j, i) = f;
+        if (writer) V(j, i) = f;
         g = e[j] + V(j, j) * f;
         for (int k = j + 1; k <= i - 1; ++k) {
           g += V(k, j) * d[k];
@@ -1455,12 +1464,17 @@ __device__ void sym_eig_smallest4(Mat V, double (&out)[4][N], int sub, unsigned 
       for (int j = 0; j < i; ++j) {
         f = d[j];
         g = e[j];
-        for (int k = j; k <= i - 1; ++k) V(k, j) -= (f * e[k] + g * d[k]);
-        d[j] = V(i - 1, j);
-        V(i, j) = 0.0;
+        // the one updated entry every lane needs back; read before lane 0 rewrites the column
+        const double last = V(i - 1, j) - (f * e[i - 1] + g * d[i - 1]);
+        if constexpr (kShared) __syncwarp(gmask);
+        // shared matrix: the four lanes split the rows of the column (d, e are replicated in their registers)
+        for (int k = j + (kShared ? sub : 0); k <= i - 1; k += (kShared ? 4 : 1)) V(k, j) -= (f * e[k] + g * d[k]);
+        if (writer) V(i, j) = 0.0;
+        d[j] = last;  // = V(i - 1, j)
       }
     }
     d[i] = h;
+    if constexpr (kShared) __syncwarp(gmask);
   }
   // reflector m (m >= 1) acts on coordinates 0..m-1: u = V(0..m-1, m), h = hs[m]; T = tridiag(diag, e[1..])
   double tnorm = 0.0;

@@ -29,6 +29,20 @@ for kw in ({}, {"adaptive": True}, {"refine": "lm"}):
     out = st(fr.heatmaps, fr.center, fr.scale)
     dev = st(torch.from_numpy(fr.heatmaps).cuda(), torch.from_numpy(fr.center).cuda(), torch.from_numpy(fr.scale).cuda())
     torch.cuda.synchronize()
+# software-pipelined executor: background tail (whole-SM CTAs, per-frame shared matrices) on a side stream
+from spe_b200.pipeline import StreamedHeatmapToPose  # noqa: E402
+
+st = HeatmapToPose(m, hypotheses=96)
+pipe = StreamedHeatmapToPose(st, 48, depth=2)
+dhm, dc, ds = torch.from_numpy(fr.heatmaps).cuda(), torch.from_numpy(fr.center).cuda(), torch.from_numpy(fr.scale).cuda()
+for _ in range(3):
+    slot = pipe.submit(dhm, dc, ds)
+pipe.drain()
+torch.cuda.synchronize()
+# the Jacobi-SVD eigen stage (SPE_FLAG_JACOBI_SVD)
+kp = slot["out"].kpts.clone()
+st.solver.solve(kp, hypotheses=96, eig="jacobi")
+torch.cuda.synchronize()
 h = spe_b200.models.hubble_synthetic(24)
 fr = spe_b200.synth.make_frames(h, 8, 96, 72, seed=4, z_range=(3.0, 8.0))
 HeatmapToPose(h, hypotheses=64)(fr.heatmaps, fr.center, fr.scale)
