@@ -313,6 +313,160 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_bulk_kernel(const Decod
 }
 
 // ------------------------------------------------------------------------------------------
+// Dynamically scheduled variant of the above (the default): same per-warp stage, bulk copy, consume
+// and batched epilogue, but a warp CLAIMS its next map from a global counter instead of owning the
+// fixed sequence gwarp, gwarp + n_warps, ...  A persistent kernel with a static split finishes when
+// its slowest CTA does; when part of the chip is busy with another kernel (the previous batch's refit
+// tail holds whole SMs for ~0.2 ms, an HRNet forward would do the same) the CTAs that have to wait for
+// an SM arrive to find their share already decoded by the others.  Costs nothing when the kernel has
+// the chip to itself: the claim for the map after next is issued right behind the bulk copy of the
+// next one, so its L2 round trip hides under the copy.
+//   counter protocol: every warp claims until it draws an index >= n_maps, i.e. exactly
+//   n_maps + (number of warps) claims per launch; atomicInc wraps at that total, so the counter is
+//   back at 0 when the launch ends and needs no reset between stream-ordered launches.
+struct PendingDyn {
+  float v;
+  int idx;
+  float nb[4];
+  int map;
+  int pad_;
+};
+
+template <int kWarps, int kChunk, int kBatch>
+struct DynLayout {
+  static constexpr size_t ring_bytes = (size_t)kWarps * kChunk * sizeof(float);
+  static constexpr size_t pend_bytes = (size_t)kWarps * kBatch * sizeof(PendingDyn);
+  static constexpr size_t bar_bytes = (size_t)kWarps * sizeof(uint64_t);
+  static constexpr size_t total = ring_bytes + pend_bytes + bar_bytes;
+};
+
+template <int kWarps, int kChunk, int kBatch>
+__global__ void __launch_bounds__(kWarps * 32, 1) decode_dyn_kernel(const DecodeArgs a, unsigned* __restrict__ counter) {
+  static_assert(kBatch <= 32, "one pending map per lane");
+  using Layout = DynLayout<kWarps, kChunk, kBatch>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* stage = reinterpret_cast<float*>(smem_raw) + (size_t)warp * kChunk;
+  PendingDyn* pend = reinterpret_cast<PendingDyn*>(smem_raw + Layout::ring_bytes) + warp * kBatch;
+  uint64_t* bar_ptr = reinterpret_cast<uint64_t*>(smem_raw + Layout::ring_bytes + Layout::pend_bytes) + warp;
+  const uint32_t bar = smem_u32(bar_ptr);
+
+  const int hw = a.H * a.W;
+  const int chunks_per_map = (hw + kChunk - 1) / kChunk;
+  const bool single = chunks_per_map == 1;
+  const unsigned wrap = (unsigned)a.n_maps + gridDim.x * kWarps - 1u;  // atomicInc: old >= wrap ? 0 : old + 1
+
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  const uint64_t policy = evict_first_policy();
+  auto claim = [&]() -> int {  // lane 0 only; >= n_maps: nothing left (and this warp must not claim again)
+    return (int)atomicInc(counter, wrap);
+  };
+  auto issue = [&](int map, int ci) {  // lane 0 only
+    const int off = ci * kChunk;
+    const int n = min(kChunk, hw - off);
+    mbar_expect_tx(bar, (uint32_t)n * 4u);
+    bulk_g2s(smem_u32(stage), a.hm + (size_t)map * hw + off, (uint32_t)n * 4u, bar, policy);
+  };
+  auto flush = [&](int count) {
+    __syncwarp();
+    if (lane < count) {
+      const PendingDyn p = pend[lane];
+      if (single) {
+        finish_map(a, p.map, p.v, p.idx, [&](float& l, float& r, float& u, float& d) { l = p.nb[0], r = p.nb[1], u = p.nb[2], d = p.nb[3]; });
+      } else {
+        const float* g = a.hm + (size_t)p.map * hw + p.idx;
+        finish_map(a, p.map, p.v, p.idx, [&](float& l, float& r, float& u, float& d) {
+          l = __ldg(g - 1), r = __ldg(g + 1), u = __ldg(g - a.W), d = __ldg(g + a.W);
+        });
+      }
+    }
+    __syncwarp();
+  };
+
+  // lane 0 holds the schedule: the map in flight and the one claimed for afterwards
+  int cur = a.n_maps, nxt = a.n_maps;
+  if (lane == 0) {
+    cur = claim();
+    if (cur < a.n_maps) {
+      issue(cur, 0);
+      nxt = claim();
+    }
+  }
+  cur = __shfl_sync(kFull, cur, 0);
+
+  Best acc[4];
+  int n_pend = 0;
+  unsigned phase = 0;
+  while (cur < a.n_maps) {
+    for (int ci = 0; ci < chunks_per_map; ++ci) {
+      const int off = ci * kChunk;
+      const int n = min(kChunk, hw - off);
+      if (ci == 0) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = Best{-INFINITY, kNoIndex};
+      }
+      mbar_wait(bar, phase & 1u);
+      ++phase;
+      const int nvec = n >> 2;
+      const float4* v4 = reinterpret_cast<const float4*>(stage);
+      int ebase = off + 4 * lane;
+#pragma unroll 4
+      for (int v = lane; v < nvec; v += 32, ebase += 128) {
+        const float4 q = v4[v];
+        take(acc[0], q.x, ebase);
+        take(acc[1], q.y, ebase);
+        take(acc[2], q.z, ebase);
+        take(acc[3], q.w, ebase);
+      }
+      const bool last = ci == chunks_per_map - 1;
+      if (last) {
+        const bool owns = 4 * lane < hw;  // a lane that never saw a value above -inf still owns its first element
+        Best b{acc[0].v, acc[0].i == kNoIndex ? 4 * lane : acc[0].i};
+#pragma unroll
+        for (int k = 1; k < 4; ++k) merge(b, acc[k].v, (acc[k].i == kNoIndex ? 4 * lane : acc[k].i) + k);
+        if (!owns) b = Best{-INFINITY, kNoIndex};
+        b = warp_merge(b);
+        if (b.v != b.v) b.i = first_nan_index(a.hm + (size_t)cur * hw, hw, lane);
+        if (lane == 0) {
+          pend[n_pend].v = b.v;
+          pend[n_pend].idx = b.i;
+          pend[n_pend].map = cur;
+        }
+        if (single && lane < 4) {
+          // clamped so the read stays inside the stage; finish_map ignores it when out of range
+          const int d = (lane == 0) ? -1 : (lane == 1) ? 1 : (lane == 2) ? -a.W : a.W;
+          pend[n_pend].nb[lane] = stage[min(max(b.i + d, 0), hw - 1)];
+        }
+        ++n_pend;
+      }
+      __syncwarp();  // every lane is done with the stage
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before the async overwrite
+        if (!last) {
+          issue(cur, ci + 1);
+        } else {
+          cur = nxt;
+          if (cur < a.n_maps) {
+            issue(cur, 0);
+            nxt = claim();
+          }
+        }
+      }
+      if (last) cur = __shfl_sync(kFull, cur, 0);
+    }
+    if (n_pend == kBatch) {
+      flush(kBatch);
+      n_pend = 0;
+    }
+  }
+  if (n_pend > 0) flush(n_pend);
+}
+
+// ------------------------------------------------------------------------------------------
 // Team variant for FEW, LARGE maps (the reference's 384x384 / 768x768 heatmaps at small batch):
 // with one warp per map a batch of 8 x 11 maps would keep 13 SMs busy.  Here a CTA owns a map, its
 // warps stream interleaved 16 KB chunks of it (same bulk-copy + mbarrier mechanics, one stage per
@@ -559,6 +713,45 @@ cudaError_t launch_bulk(const DecodeArgs& a, int dev, int num_sms, cudaStream_t 
   return cudaGetLastError();
 }
 
+// per-device claim counters for decode_dyn_kernel: a small ring, so that launches in flight on different
+// streams do not share one (stream-ordered launches may: the counter is back at 0 when a launch ends)
+constexpr int kDynCounters = 16;
+inline cudaError_t dyn_counter(int dev, unsigned** out) {
+  static unsigned* base[kMaxDevices] = {};
+  static std::atomic<unsigned> next[kMaxDevices];
+  static PerDeviceOnce once;
+  const cudaError_t e = once.run(dev, [dev] {
+    unsigned* p = nullptr;
+    cudaError_t r = cudaMalloc(&p, sizeof(unsigned) * kDynCounters * 32);  // one counter per 128 B line
+    if (r == cudaSuccess) r = cudaMemset(p, 0, sizeof(unsigned) * kDynCounters * 32);
+    if (r == cudaSuccess) base[dev] = p;
+    return r;
+  });
+  if (e != cudaSuccess) return e;
+  *out = base[dev] + 32 * (next[dev].fetch_add(1, std::memory_order_relaxed) % kDynCounters);
+  return cudaSuccess;
+}
+
+template <int kWarps, int kChunk, int kBatch = 32>
+cudaError_t launch_dyn(const DecodeArgs& a, int dev, int num_sms, cudaStream_t stream) {
+  constexpr size_t smem = DynLayout<kWarps, kChunk, kBatch>::total;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
+  static PerDeviceOnce once;
+  cudaError_t e = once.run(dev, [] {
+    cudaError_t r = cudaFuncSetAttribute(decode_dyn_kernel<kWarps, kChunk, kBatch>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(decode_dyn_kernel<kWarps, kChunk, kBatch>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    return r;
+  });
+  if (e != cudaSuccess) return e;
+  unsigned* counter = nullptr;
+  e = dyn_counter(dev, &counter);
+  if (e != cudaSuccess) return e;
+  const int ctas_needed = (a.n_maps + kWarps - 1) / kWarps;
+  const int grid = ctas_needed < num_sms ? ctas_needed : num_sms;
+  decode_dyn_kernel<kWarps, kChunk, kBatch><<<grid, kWarps * 32, smem, stream>>>(a, counter);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 // dev knob (SPE_DECODE_VARIANT): picks the warps x stages x chunk shape measured in profiles/decode_variants_r1.md
@@ -608,7 +801,9 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
       // 112 KB of bulk copies in flight per SM; 64x64 maps refine from shared memory.  The 132 KB
       // carveout (58 %) is the one the pose kernels use too, so an SM never has to drain to switch
       // its shared-memory/L1 split when the kernels of consecutive batches overlap.
-      default: return launch_bulk<7, 1, 4096, 32, kSmemCarveoutPct>(a, dev, num_sms, stream);
+      case 7: return launch_bulk<7, 1, 4096, 32, kSmemCarveoutPct>(a, dev, num_sms, stream);  // same shape, static split of the maps
+      // default: that shape with the maps claimed dynamically (decode_dyn_kernel)
+      default: return launch_dyn<7, 4096>(a, dev, num_sms, stream);
     }
   }
   const int ctas_needed = (a.n_maps + kPlainWarps - 1) / kPlainWarps;

@@ -198,17 +198,17 @@ class StreamedHeatmapToPose:
     size, occupying about one warp per SM).  Submitting batch i+1's front on the main stream while
     batch i's tail (and the final all_gather of its poses) runs on a side stream hides the tail:
     spe_ransac_score_f32 / spe_ransac_select_refit_f32 are the two halves of the C ABI call.
-    Results of a submit() are valid once its `done` event has completed (wait(), or stream order
-    on the side stream).  `depth` batches are in flight, each with its own buffers.
+    Results of a submit() are valid after wait(slot) or drain().  `depth` batches are in flight, each with its own buffers.
     """
 
-    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 2, gather_total: int | None = None, want_rt: bool = False):
+    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 2, gather_total: int | None = None, want_rt: bool = False,
+                 tail_after_decode: bool = False, tail_priority: int = 0):
         torch = stage._torch
         self.stage, self.B, self.depth, self.gather_total = stage, int(batch), int(depth), gather_total
         dev, J, H = stage.device, stage.solver.J, stage.hypotheses
         self._L = stage._L
         self.main = torch.cuda.current_stream(dev)
-        self.side = torch.cuda.Stream(dev)  # (a high-priority side stream changes nothing: measured)
+        self.side = torch.cuda.Stream(dev, priority=tail_priority)  # (priority makes no measurable difference)
         self.ws_bytes = int(self._L.spe_ransac_workspace_bytes(stage.solver.handle, self.B, H))
         self.slots = []
         for _ in range(self.depth):
@@ -219,21 +219,26 @@ class StreamedHeatmapToPose:
                                    torch.empty((self.B,), dtype=torch.int32, device=dev), torch.empty((self.B, J, 3), dtype=torch.float32, device=dev)),
                 "rt": torch.empty((self.B, 12), dtype=torch.float64, device=dev) if want_rt else None,
                 "ws": torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev),
-                "scored": torch.cuda.Event(), "done": done, "gathered": None,
+                "scored": torch.cuda.Event(), "decoded": torch.cuda.Event(), "done": done, "gathered": None,
             })
         self._next = 0
+        self._pending = None
+        self.tail_after_decode = bool(tail_after_decode)
 
     def submit(self, hm, center, scale, decode_events=None):
         """Enqueue one batch.  Returns the slot dict: slot['out'] (StageOutput), slot['gathered']
-        (the [N_total,7] tensor if gather_total was given), slot['done'] (event)."""
+        (the [N_total,7] tensor if gather_total was given), slot['done'] (event).  The batch's tail is
+        enqueued by the NEXT submit() (behind that batch's decode), or by wait()/drain()."""
         torch = self.stage._torch
         st = self.stage
         B, J, H, W = hm.shape
         assert B == self.B and J == st.solver.J and hm.is_contiguous() and hm.dtype == torch.float32
         slot = self.slots[self._next]
         self._next = (self._next + 1) % self.depth
+        if slot is self._pending:  # depth 1: this slot's previous tail has to run first
+            self.flush()
         out, ws = slot["out"], slot["ws"]
-        main, side = self.main, self.side
+        main = self.main
         main.wait_event(slot["done"])  # the tail that last used this slot's buffers has finished
         if decode_events is not None:
             decode_events[0].record(main)
@@ -241,11 +246,28 @@ class StreamedHeatmapToPose:
                                                out.kpts.data_ptr(), None, main.cuda_stream), "spe_decode_kpts_f32")
         if decode_events is not None:
             decode_events[1].record(main)
+        slot["decoded"].record(main)
+        # tail_after_decode: the previous batch's tail is enqueued behind THIS batch's decode, so that the decode has
+        # every SM to itself (0.115 ms instead of 0.150 in the step) — but the step is slower that way (0.745 vs
+        # 0.707 ms, tools/pipe_ab.py): the dynamically scheduled decode tolerates the tail's whole-SM CTAs well, and
+        # the tail hides better under decode + hypotheses than under the hypotheses alone.  Off by default.
+        if self._pending is not None:
+            self._enqueue_tail(self._pending, after=slot["decoded"] if self.tail_after_decode else None)
         _lib.check(self._L.spe_ransac_score_f32(st.solver.handle, out.kpts.data_ptr(), B, st.hypotheses, st.reproj_err, st.confidence,
                                                 st.conf_floor, ws.data_ptr(), ws.numel(), st.flags, main.cuda_stream), "spe_ransac_score_f32")
         slot["scored"].record(main)
+        self._pending = slot
+        if not self.tail_after_decode:
+            self.flush()
+        return slot
+
+    def _enqueue_tail(self, slot, after=None):
+        torch = self.stage._torch
+        st, side, out, ws = self.stage, self.side, slot["out"], slot["ws"]
         side.wait_event(slot["scored"])
-        _lib.check(self._L.spe_ransac_select_refit_f32(st.solver.handle, B, st.hypotheses, st.confidence, out.pose7.data_ptr(),
+        if after is not None:
+            side.wait_event(after)
+        _lib.check(self._L.spe_ransac_select_refit_f32(st.solver.handle, self.B, st.hypotheses, st.confidence, out.pose7.data_ptr(),
                                                        out.inlier_mask.data_ptr(), out.status.data_ptr(), None,
                                                        slot["rt"].data_ptr() if slot["rt"] is not None else None, ws.data_ptr(), ws.numel(),
                                                        st.flags | _lib.FLAG_BACKGROUND_TAIL, side.cuda_stream), "spe_ransac_select_refit_f32")
@@ -253,9 +275,20 @@ class StreamedHeatmapToPose:
             with torch.cuda.stream(side):
                 slot["gathered"] = all_gather_rows(out.pose7, self.gather_total)
         slot["done"].record(side)
-        return slot
+        self._pending = None
+
+    def flush(self):
+        """Enqueue the tail of the most recent batch now (nothing follows it to hide behind)."""
+        if self._pending is not None:
+            self._enqueue_tail(self._pending)
+
+    def wait(self, slot):
+        """Block the host until the results of `slot` are complete."""
+        self.flush()
+        slot["done"].synchronize()
 
     def drain(self):
         """Make the main stream wait for every tail in flight."""
+        self.flush()
         for slot in self.slots:
             self.main.wait_event(slot["done"])

@@ -142,7 +142,7 @@ def test_streamed_executor_matches_single_calls():
     got = []
     for hm, c, s in batches:
         slot = pipe.submit(hm, c, s)
-        slot["done"].synchronize()  # results of a slot are only valid until it is reused
+        pipe.wait(slot)  # results of a slot are only valid until it is reused
         o = slot["out"]
         got.append((o.pose7.clone(), o.inlier_mask.clone(), o.status.clone(), o.kpts.clone()))
     # and without synchronising in between (the executor must protect its own buffers)

@@ -66,15 +66,16 @@ timeit(lambda: (decode(), score()), "front (decode + score)")
 timeit(lambda: tail(0), "tail, shared-memory matrix")
 timeit(lambda: tail(_lib.FLAG_BACKGROUND_TAIL), "tail, background variant")
 timeit(lambda: (decode(), score(), tail(0)), "serial, one stream")
+for tad in (False, True):
+    for prio in (0, -1):
+        pipe = StreamedHeatmapToPose(stage, B, depth=2, tail_after_decode=tad, tail_priority=prio)
+
+        def piped():
+            pipe.submit(hm, c, s)
+
+        timeit(piped, f"pipelined tad={int(tad)} prio={prio}")
+        pipe.drain()
 pipe = StreamedHeatmapToPose(stage, B, depth=2)
-
-
-def piped():
-    pipe.submit(hm, c, s)
-
-
-timeit(piped, "pipelined (2 streams)")
-pipe.drain()
 torch.cuda.synchronize()
 # CUDA graph of 10 pipelined steps
 g = torch.cuda.CUDAGraph()
