@@ -307,6 +307,84 @@ __device__ __forceinline__ void gauss_newton_doubled(const float (&L)[6][10], co
   }
 }
 
+// The five steps for NB beta vectors at once (the three variants of one hypothesis).  The 6x4 system of a
+// step is never stored: each Jacobian row goes straight into the packed normal equations G (10) and y (4),
+// and the NB Cholesky factorisations / substitutions — short loops dominated by dependent rsqrt and FMA
+// chains — run interleaved, which is the point: NB independent chains per thread for the scheduler.
+template <int NB>
+__device__ __forceinline__ void gauss_newton_doubled_batch(const float (&L)[6][10], const float (&rho)[6], float (&be)[NB][4]) {
+#pragma unroll 1
+  for (int it = 0; it < 5; ++it) {
+    float G[NB][4][4], y[NB][4];  // upper triangles only
+#pragma unroll
+    for (int m = 0; m < NB; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        y[m][i] = 0.f;
+#pragma unroll
+        for (int j = i; j < 4; ++j) G[m][i][j] = 0.f;
+      }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float* l = L[k];
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        const float* b = be[m];
+        float a[4];
+        a[0] = fmaf(l[6], b[3], fmaf(l[3], b[2], fmaf(l[1], b[1], l[0] * b[0])));
+        a[1] = fmaf(l[7], b[3], fmaf(l[4], b[2], fmaf(l[2], b[1], l[1] * b[0])));
+        a[2] = fmaf(l[8], b[3], fmaf(l[5], b[2], fmaf(l[4], b[1], l[3] * b[0])));
+        a[3] = fmaf(l[9], b[3], fmaf(l[8], b[2], fmaf(l[7], b[1], l[6] * b[0])));
+        const float q2 = fmaf(a[3], b[3], fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])));
+        const float r = fmaf(-0.5f, q2, rho[k]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          y[m][i] = fmaf(a[i], r, y[m][i]);
+#pragma unroll
+          for (int j = i; j < 4; ++j) G[m][i][j] = fmaf(a[i], a[j], G[m][i][j]);
+        }
+      }
+    }
+    // Cholesky G = U^T U in place (inv = 1 / U_ii), U^T z = y, U x = z; m innermost
+    float inv[NB][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        float dgn = G[m][i][i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) dgn = fmaf(-G[m][k][i], G[m][k][i], dgn);
+        inv[m][i] = dgn > Real<float>::tiny ? rsqrt_approx(dgn) : 0.f;
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) {
+          float acc = G[m][i][j];
+#pragma unroll
+          for (int k = 0; k < i; ++k) acc = fmaf(-G[m][k][i], G[m][k][j], acc);
+          G[m][i][j] = acc * inv[m][i];
+        }
+        float z = y[m][i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) z = fmaf(-G[m][k][i], y[m][k], z);
+        y[m][i] = z * inv[m][i];
+      }
+    }
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+#pragma unroll
+      for (int m = 0; m < NB; ++m) {
+        float acc = y[m][i];
+#pragma unroll
+        for (int j = i + 1; j < 4; ++j) acc = fmaf(-G[m][i][j], y[m][j], acc);
+        y[m][i] = acc * inv[m][i];  // y now holds x
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < NB; ++m)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) be[m][i] += y[m][i];
+  }
+}
+
 // R = U V^T of the 3x3 matrix A = U S V^T (orthogonal Procrustes factor), by one-sided Jacobi.
 // The left vector of the smallest singular value is rebuilt as a cross product so that nearly
 // planar configurations stay orthonormal; its sign follows the rotated column, which preserves

@@ -832,29 +832,30 @@ __device__ __forceinline__ void eig_qr_inverse_iteration(float (&A)[12][10], flo
   float w1[10] = {0.6f, 0.85f, -0.45f, 0.35f, 0.75f, -0.9f, -0.5f, 0.55f, 0.4f, -0.8f};
 #pragma unroll 1
   for (int it = 0; it < iters; ++it) {
+    // Both substitutions in their column-oriented (axpy) form: once an unknown is final it is eliminated from
+    // all the remaining equations with independent FMAs, so the dependent chain is 10 x (mul, fma) instead of
+    // the 55 serial FMAs of the row-oriented loops.
     // R a = w (back substitution), in place
 #pragma unroll
-    for (int i = 9; i >= 0; --i) {
-      float a0 = w0[i], a1 = w1[i];
+    for (int j = 9; j >= 0; --j) {
+      w0[j] *= rinv[j];
+      w1[j] *= rinv[j];
 #pragma unroll
-      for (int j = i + 1; j < 10; ++j) {
-        a0 = fmaf(-A[i][j], w0[j], a0);
-        a1 = fmaf(-A[i][j], w1[j], a1);
+      for (int i = 0; i < j; ++i) {
+        w0[i] = fmaf(-A[i][j], w0[j], w0[i]);
+        w1[i] = fmaf(-A[i][j], w1[j], w1[i]);
       }
-      w0[i] = a0 * rinv[i];
-      w1[i] = a1 * rinv[i];
     }
     // R^T y = a (forward substitution), in place
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
-      float a0 = w0[i], a1 = w1[i];
+    for (int j = 0; j < 10; ++j) {
+      w0[j] *= rinv[j];
+      w1[j] *= rinv[j];
 #pragma unroll
-      for (int j = 0; j < i; ++j) {
-        a0 = fmaf(-A[j][i], w0[j], a0);
-        a1 = fmaf(-A[j][i], w1[j], a1);
+      for (int i = j + 1; i < 10; ++i) {
+        w0[i] = fmaf(-A[j][i], w0[j], w0[i]);
+        w1[i] = fmaf(-A[j][i], w1[j], w1[i]);
       }
-      w0[i] = a0 * rinv[i];
-      w1[i] = a1 * rinv[i];
     }
     // Gram-Schmidt
     float n0 = 0.f, d01 = 0.f;
@@ -1143,21 +1144,22 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
       }
 #pragma unroll
     for (int c = 0; c < 3; ++c) pw0[c] *= 0.2f;
-    // Gauss-Newton per variant (one after the other: it keeps L and its own 6x4 system live); the 3x3
-    // cross-covariances are parked so that the three Procrustes problems run interleaved afterwards.
-    float abt_all[3][3][3] = {}, pc0_all[3][3] = {};
-#pragma unroll 1
-    for (int variant = 1; variant <= 3; ++variant) {
-      float betas[4];
-      approx_betas<float, true, true>(L, rho, variant, betas);
-      gauss_newton_doubled(L, rho, betas);
+    // The three beta variants side by side: initialisation, five Gauss-Newton steps (interleaved), then the
+    // camera-frame control points and the 3x3 cross-covariance of each, for the interleaved Procrustes.
+    float betas[3][4];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) approx_betas<float, true, true>(L, rho, v + 1, betas[v]);
+    gauss_newton_doubled_batch<3>(L, rho, betas);
+    float abt_all[3][3][3], pc0_all[3][3];
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
       float ccs[4][3];
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
-          ccs[j][c] = betas[0] * work[3 * j + c] + betas[1] * work[12 + 3 * j + c] + betas[2] * work[24 + 3 * j + c] +
-                      betas[3] * work[36 + 3 * j + c];
+          ccs[j][c] = betas[v][0] * work[3 * j + c] + betas[v][1] * work[12 + 3 * j + c] + betas[v][2] * work[24 + 3 * j + c] +
+                      betas[v][3] * work[36 + 3 * j + c];
       float pcs[5][3];
 #pragma unroll
       for (int k = 0; k < 5; ++k)
@@ -1166,34 +1168,27 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
           pcs[k][c] = work[48 + 4 * k] * ccs[0][c] + work[48 + 4 * k + 1] * ccs[1][c] + work[48 + 4 * k + 2] * ccs[2][c] +
                       work[48 + 4 * k + 3] * ccs[3][c];
       const float sgn = pcs[0][2] < 0.f ? -1.f : 1.f;
-      float pc0[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 3; ++c) pc0_all[v][c] = 0.f;
 #pragma unroll
       for (int k = 0; k < 5; ++k)
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           pcs[k][c] *= sgn;
-          pc0[c] += pcs[k][c];
+          pc0_all[v][c] += pcs[k][c];
         }
 #pragma unroll
-      for (int c = 0; c < 3; ++c) pc0[c] *= 0.2f;
-      float abt[3][3] = {};
+      for (int c = 0; c < 3; ++c) pc0_all[v][c] *= 0.2f;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) abt_all[v][r][c] = 0.f;
 #pragma unroll
       for (int k = 0; k < 5; ++k)
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int c = 0; c < 3; ++c) abt[r][c] = fmaf(pcs[k][r] - pc0[r], pw[k][c] - pw0[c], abt[r][c]);
-      // static register indices only: select into the slot of this variant
-#pragma unroll
-      for (int v = 0; v < 3; ++v) {
-        const bool mine = variant == v + 1;
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) abt_all[v][r][c] = mine ? abt[r][c] : abt_all[v][r][c];
-          pc0_all[v][r] = mine ? pc0[r] : pc0_all[v][r];
-        }
-      }
+          for (int c = 0; c < 3; ++c) abt_all[v][r][c] = fmaf(pcs[k][r] - pc0_all[v][r], pw[k][c] - pw0[c], abt_all[v][r][c]);
     }
     float R_all[3][3][3];
     procrustes_uvt_batch<3>(abt_all, R_all);
