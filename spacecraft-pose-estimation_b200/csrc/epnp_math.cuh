@@ -284,29 +284,9 @@ __device__ __forceinline__ void gauss_newton(const T (&L)[6][10], const T (&rho)
   }
 }
 
-// The same five steps for the FP32 hypothesis path, on L with doubled squared terms (build_L<T, true>):
-// Jacobian row k = four 4-term dot products, and beta^T Q_k beta = (J_k . beta) / 2 gives the residual
-// from it (126 instead of 204 instructions per step).
-__device__ __forceinline__ void gauss_newton_doubled(const float (&L)[6][10], const float (&rho)[6], float (&be)[4]) {
-#pragma unroll 1
-  for (int it = 0; it < 5; ++it) {
-    float A[6][4], r[6], x[4];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const float* l = L[k];
-      A[k][0] = fmaf(l[6], be[3], fmaf(l[3], be[2], fmaf(l[1], be[1], l[0] * be[0])));
-      A[k][1] = fmaf(l[7], be[3], fmaf(l[4], be[2], fmaf(l[2], be[1], l[1] * be[0])));
-      A[k][2] = fmaf(l[8], be[3], fmaf(l[5], be[2], fmaf(l[4], be[1], l[3] * be[0])));
-      A[k][3] = fmaf(l[9], be[3], fmaf(l[8], be[2], fmaf(l[7], be[1], l[6] * be[0])));
-      const float q2 = fmaf(A[k][3], be[3], fmaf(A[k][2], be[2], fmaf(A[k][1], be[1], A[k][0] * be[0])));
-      r[k] = fmaf(-0.5f, q2, rho[k]);
-    }
-    lsq_normal<float, 6, 4>(A, r, x);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) be[i] += x[i];
-  }
-}
-
+// FP32 hypothesis path: L comes with doubled squared terms (build_L<T, true>), so a Jacobian row is four plain
+// 4-term dot products and beta^T Q_k beta = (J_k . beta) / 2 gives the residual from it (126 instead of 204
+// instructions per step).
 // The five steps for NB beta vectors at once (the three variants of one hypothesis).  The 6x4 system of a
 // step is never stored: each Jacobian row goes straight into the packed normal equations G (10) and y (4),
 // and the NB Cholesky factorisations / substitutions — short loops dominated by dependent rsqrt and FMA
