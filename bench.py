@@ -40,7 +40,7 @@ WORKLOAD = "SPEED+ Tango 11 landmarks, 64x64 heatmaps, batch 4096 per GPU, 256 R
 # SURVEY §8(d) algorithmic work
 DECODE_BYTES_PER_FRAME = J * HM_H * HM_W * 4 + J * 12 + 16
 HYP_FLOPS = 126_400 + 54 * J  # canonical FP32 flops per hypothesis at n = J
-HYP_WARP_INSTR_PER_LAUNCH = 435_774_489 + 6_201_344  # ncu smsp__inst_executed.sum: hypothesis_kernel_t1 + frame_prep_kernel, 4096 frames x 256
+HYP_WARP_INSTR_PER_LAUNCH = 407_234_487 + 6_201_344  # ncu smsp__inst_executed.sum: hypothesis_kernel_t1 + frame_prep_kernel, 4096 frames x 256
 
 
 def config_dict(n_gpus):
@@ -358,7 +358,7 @@ def gpu_arm(args, rank, local_rank, world):
                        "unit": "G warp-instructions/s", "frac": issue_rate / issue_peak, "ms_per_launch": score_ms,
                        "warp_instructions_per_launch": HYP_WARP_INSTR_PER_LAUNCH,
                        "note": "FP32 CUDA-core work with no dense contraction: the bound is the instruction issue rate (148 SMs x 4 schedulers x clock). "
-                               "Executed warp-instructions per 4096 x 256 launch are ncu's smsp__inst_executed.sum (profiles/step_r1_ncu_raw.txt; 60 % of them "
+                               "Executed warp-instructions per 4096 x 256 launch are ncu's smsp__inst_executed.sum (profiles/step_r1_ncu_raw.txt; 62 % of them "
                                "on the FMA pipe); duration measured here with CUDA events",
                        "select_refit_ms_per_call": solve_ms - score_ms, "solve_ms_per_call": solve_ms,
                        "canonical_tflops": canonical_tflops, "flops_per_hypothesis": HYP_FLOPS,
