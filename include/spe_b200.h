@@ -83,6 +83,15 @@ int spe_decode_kpts_f32(const float* hm, int B, int J, int H, int W, const float
                         const float* scale, int post_process, float* kpts, int32_t* argmax,
                         void* stream);
 
+/* spe_decode_kpts_f32 with flags.  SPE_DECODE_BACKGROUND: the caller runs this decode on its own stream UNDER a
+ * compute-bound kernel of another stream (the hypothesis scoring of the previous batch): it is launched as small CTAs
+ * (3 warps, 51 KB of shared memory) that take the place of one hypothesis CTA per SM as those retire, instead of the
+ * 7-warp / 113 KB CTAs that want an SM's shared memory to themselves.  Same results. */
+#define SPE_DECODE_BACKGROUND 1
+int spe_decode_kpts_ex_f32(const float* hm, int B, int J, int H, int W, const float* center,
+                           const float* scale, int post_process, float* kpts, int32_t* argmax,
+                           int flags, void* stream);
+
 /* Decode of a combination of K heatmap tensors that is never written to memory.
  * srcs: HOST array of K DEVICE pointers, each [B,J,H,W] float32.
  *   SPE_COMBINE_MEAN  ((src0 + src1) + ... ) * (1/K)          model ensemble, validate_cv,

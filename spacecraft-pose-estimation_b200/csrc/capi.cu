@@ -18,7 +18,7 @@ int cuda_fail(cudaError_t e) {
 }
 
 int run_decode(const float* hm, int B, int J, int H, int W, const float* center, const float* scale, int post_process,
-               float* preds, float* maxvals, float* kpts, int32_t* argmax, void* stream) {
+               float* preds, float* maxvals, float* kpts, int32_t* argmax, void* stream, int background = 0) {
   if (B < 0 || J <= 0 || H <= 0 || W <= 0) return SPE_ERR_INVALID_ARGUMENT;
   if ((long long)H * W > 0x7fffffffLL || (long long)B * J > 0x7fffffffLL) return SPE_ERR_INVALID_ARGUMENT;
   if (B == 0) return SPE_OK;
@@ -38,6 +38,7 @@ int run_decode(const float* hm, int B, int J, int H, int W, const float* center,
   a.maxvals = maxvals;
   a.kpts = kpts;
   a.argmax = argmax;
+  a.background = background;
   const cudaError_t e = spe::launch_decode(a, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
@@ -73,8 +74,13 @@ int spe_decode_f32(const float* hm, int B, int J, int H, int W, const float* cen
 
 int spe_decode_kpts_f32(const float* hm, int B, int J, int H, int W, const float* center, const float* scale, int post_process,
                         float* kpts, int32_t* argmax, void* stream) {
+  return spe_decode_kpts_ex_f32(hm, B, J, H, W, center, scale, post_process, kpts, argmax, 0, stream);
+}
+
+int spe_decode_kpts_ex_f32(const float* hm, int B, int J, int H, int W, const float* center, const float* scale, int post_process,
+                           float* kpts, int32_t* argmax, int flags, void* stream) {
   if (center == nullptr || scale == nullptr || kpts == nullptr) return B == 0 ? SPE_OK : SPE_ERR_INVALID_ARGUMENT;
-  return run_decode(hm, B, J, H, W, center, scale, post_process, nullptr, nullptr, kpts, argmax, stream);
+  return run_decode(hm, B, J, H, W, center, scale, post_process, nullptr, nullptr, kpts, argmax, stream, (flags & SPE_DECODE_BACKGROUND) ? 1 : 0);
 }
 
 int spe_decode_combined_kpts_f32(const float* const* srcs, int K, int mode, const int32_t* flip_perm, int shift_heatmap, int B, int J, int H, int W,

@@ -789,6 +789,13 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
       return cudaGetLastError();
     }
   }
+  if (aligned && a.background) {
+    // 3 warps x one 16 KB stage: 51 KB of shared memory and 6.9 K registers, i.e. the footprint of ONE of the three
+    // hypothesis-kernel CTAs of an SM (39 KB, 21.5 K registers): as those retire, a decode CTA of the next batch
+    // takes the slot, streams its share of the maps while the SM's FP32 pipes stay busy with the other two, and
+    // leaves.  48 KB in flight per SM is still enough for ~6 TB/s (Little), so the slot is held only briefly.
+    return launch_dyn<3, 4096, 16>(a, dev, num_sms, stream);
+  }
   if (aligned) {
     switch (decode_variant()) {
       case 1: return launch_bulk<4, 3, 4096>(a, dev, num_sms, stream);   // 192 KB, 4 warps

@@ -6,7 +6,10 @@
 namespace spe {
 
 // Shared-memory carveout preferred by every kernel of the stage (percent of 228 KB -> 132 KB).
-constexpr int kSmemCarveoutPct = 58;
+#ifndef SPE_SMEM_CARVEOUT
+#define SPE_SMEM_CARVEOUT 58
+#endif
+constexpr int kSmemCarveoutPct = SPE_SMEM_CARVEOUT;
 
 struct DecodeArgs {
   const float* hm;      // [n_maps, H, W]
@@ -18,6 +21,7 @@ struct DecodeArgs {
   float* maxvals;   // [n_maps]
   float* kpts;      // [n_maps,3]   (x, y, maxval) or nullptr
   int32_t* argmax;  // [n_maps] or nullptr
+  int background;   // SPE_DECODE_BACKGROUND: small CTAs meant to run UNDER a compute-bound kernel of another stream
 };
 
 cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream);

@@ -44,6 +44,8 @@ def _declare(L):
     L.spe_decode_f32.argtypes = [fp, c_int, c_int, c_int, c_int, fp, fp, c_int, fp, fp, ip, c_void_p]
     L.spe_decode_kpts_f32.restype = c_int
     L.spe_decode_kpts_f32.argtypes = [fp, c_int, c_int, c_int, c_int, fp, fp, c_int, fp, ip, c_void_p]
+    L.spe_decode_kpts_ex_f32.restype = c_int
+    L.spe_decode_kpts_ex_f32.argtypes = [fp, c_int, c_int, c_int, c_int, fp, fp, c_int, fp, ip, c_int, c_void_p]
     L.spe_decode_combined_kpts_f32.restype = c_int
     L.spe_decode_combined_kpts_f32.argtypes = [POINTER(c_void_p), c_int, c_int, ip, c_int, c_int, c_int, c_int, c_int, fp, fp, c_int, fp, ip,
                                                c_void_p]
@@ -78,10 +80,11 @@ FLAG_REFINE_LM = 1
 FLAG_ADAPTIVE = 2
 FLAG_BACKGROUND_TAIL = 4
 FLAG_JACOBI_SVD = 8
+DECODE_BACKGROUND = 1
 
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",
-    "spe_decode_kpts_f32", "spe_decode_combined_kpts_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
+    "spe_decode_kpts_f32", "spe_decode_kpts_ex_f32", "spe_decode_combined_kpts_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
     "spe_pnp_model_minimal_sets", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_score_f32",
     "spe_ransac_select_refit_f32", "spe_ransac_debug_scores",
     "spe_pipeline_workspace_bytes", "spe_heatmap_to_pose_f32",

@@ -202,13 +202,20 @@ class StreamedHeatmapToPose:
     """
 
     def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 2, gather_total: int | None = None, want_rt: bool = False,
-                 tail_after_decode: bool = False, tail_priority: int = 0):
+                 tail_after_decode: bool = False, tail_priority: int = 0, overlap_decode: bool = False):
         torch = stage._torch
         self.stage, self.B, self.depth, self.gather_total = stage, int(batch), int(depth), gather_total
         dev, J, H = stage.device, stage.solver.J, stage.hypotheses
         self._L = stage._L
         self.main = torch.cuda.current_stream(dev)
         self.side = torch.cuda.Stream(dev, priority=tail_priority)  # (priority makes no measurable difference)
+        # overlap_decode: the HBM-bound decode of batch i+1 runs on its own (high-priority) stream as small background
+        # CTAs (SPE_DECODE_BACKGROUND) under the compute-bound hypothesis scoring of batch i
+        self.overlap_decode = bool(overlap_decode)
+        self.dstream = torch.cuda.Stream(dev, priority=-1) if self.overlap_decode else None
+        # ... and the scoring on an internal stream too: an event recorded on the caller's stream must cover the
+        # producer of the inputs only, not the previous batch's scoring
+        self.cstream = torch.cuda.Stream(dev) if self.overlap_decode else self.main
         self.ws_bytes = int(self._L.spe_ransac_workspace_bytes(stage.solver.handle, self.B, H))
         self.slots = []
         for _ in range(self.depth):
@@ -219,7 +226,7 @@ class StreamedHeatmapToPose:
                                    torch.empty((self.B,), dtype=torch.int32, device=dev), torch.empty((self.B, J, 3), dtype=torch.float32, device=dev)),
                 "rt": torch.empty((self.B, 12), dtype=torch.float64, device=dev) if want_rt else None,
                 "ws": torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev),
-                "scored": torch.cuda.Event(), "decoded": torch.cuda.Event(), "done": done, "gathered": None,
+                "scored": torch.cuda.Event(), "decoded": torch.cuda.Event(), "input": torch.cuda.Event(), "done": done, "gathered": None,
             })
         self._next = 0
         self._pending = None
@@ -239,23 +246,38 @@ class StreamedHeatmapToPose:
             self.flush()
         out, ws = slot["out"], slot["ws"]
         main = self.main
-        main.wait_event(slot["done"])  # the tail that last used this slot's buffers has finished
-        if decode_events is not None:
-            decode_events[0].record(main)
-        _lib.check(self._L.spe_decode_kpts_f32(hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(st.post_process),
-                                               out.kpts.data_ptr(), None, main.cuda_stream), "spe_decode_kpts_f32")
-        if decode_events is not None:
-            decode_events[1].record(main)
-        slot["decoded"].record(main)
+        if self.overlap_decode:
+            ds = self.dstream
+            slot["input"].record(main)  # whatever produced hm/center/scale on the caller's stream
+            ds.wait_event(slot["input"])
+            ds.wait_event(slot["done"])  # the tail that last used this slot's buffers has finished
+            if decode_events is not None:
+                decode_events[0].record(ds)
+            _lib.check(self._L.spe_decode_kpts_ex_f32(hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(st.post_process),
+                                                      out.kpts.data_ptr(), None, _lib.DECODE_BACKGROUND, ds.cuda_stream), "spe_decode_kpts_ex_f32")
+            if decode_events is not None:
+                decode_events[1].record(ds)
+            slot["decoded"].record(ds)
+            self.cstream.wait_event(slot["decoded"])
+        else:
+            main.wait_event(slot["done"])  # the tail that last used this slot's buffers has finished
+            if decode_events is not None:
+                decode_events[0].record(main)
+            _lib.check(self._L.spe_decode_kpts_f32(hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(st.post_process),
+                                                   out.kpts.data_ptr(), None, main.cuda_stream), "spe_decode_kpts_f32")
+            if decode_events is not None:
+                decode_events[1].record(main)
+            slot["decoded"].record(main)
         # tail_after_decode: the previous batch's tail is enqueued behind THIS batch's decode, so that the decode has
         # every SM to itself (0.115 ms instead of 0.150 in the step) — but the step is slower that way (0.745 vs
         # 0.707 ms, tools/pipe_ab.py): the dynamically scheduled decode tolerates the tail's whole-SM CTAs well, and
         # the tail hides better under decode + hypotheses than under the hypotheses alone.  Off by default.
         if self._pending is not None:
             self._enqueue_tail(self._pending, after=slot["decoded"] if self.tail_after_decode else None)
+        cs = self.cstream
         _lib.check(self._L.spe_ransac_score_f32(st.solver.handle, out.kpts.data_ptr(), B, st.hypotheses, st.reproj_err, st.confidence,
-                                                st.conf_floor, ws.data_ptr(), ws.numel(), st.flags, main.cuda_stream), "spe_ransac_score_f32")
-        slot["scored"].record(main)
+                                                st.conf_floor, ws.data_ptr(), ws.numel(), st.flags, cs.cuda_stream), "spe_ransac_score_f32")
+        slot["scored"].record(cs)
         self._pending = slot
         if not self.tail_after_decode:
             self.flush()

@@ -18,9 +18,12 @@ c, s = torch.from_numpy(fr.center).to(dev), torch.from_numpy(fr.scale).to(dev)
 stage = HeatmapToPose(model, hypotheses=HYP, device=dev)
 K = 100
 res = {}
-for rep in range(4):
-    for tad in (False, True):
-        pipe = StreamedHeatmapToPose(stage, B, depth=2, tail_after_decode=tad)
+for rep in range(3):
+    for tad in (False, "ovl2", "ovl3", "ovl4"):
+        if tad in (False, True):
+            pipe = StreamedHeatmapToPose(stage, B, depth=2, tail_after_decode=tad)
+        else:
+            pipe = StreamedHeatmapToPose(stage, B, depth=int(tad[3:]), overlap_decode=True)
         for _ in range(10):
             pipe.submit(hm, c, s)
         pipe.drain()
@@ -35,5 +38,5 @@ for rep in range(4):
         torch.cuda.synchronize()
         res.setdefault(tad, []).append((e0.elapsed_time(e1) / K, sum(a.elapsed_time(b) for a, b in dec) / K))
 for tad, v in res.items():
-    print(f"decode_variant={os.environ.get('SPE_DECODE_VARIANT', 'dyn')} tail_after_decode={int(tad)}: step ms " + " ".join(f"{x[0]:.4f}" for x in v) +
+    print(f"decode_variant={os.environ.get('SPE_DECODE_VARIANT', 'dyn')} mode={tad}: step ms " + " ".join(f"{x[0]:.4f}" for x in v) +
           " | decode-in-step ms " + " ".join(f"{x[1]:.4f}" for x in v))
