@@ -185,3 +185,11 @@ def test_streamed_executor_matches_single_calls():
     pipe2.drain()
     torch.cuda.synchronize()
     assert torch.equal(last2["out"].pose7, last["out"].pose7)
+    # decode of batch i+1 as background CTAs on its own stream under the scoring of batch i: same results
+    pipe3 = StreamedHeatmapToPose(stage, 256, depth=3, overlap_decode=True)
+    for hm, c, s in batches:
+        last3 = pipe3.submit(hm, c, s)
+    pipe3.drain()
+    torch.cuda.synchronize()
+    assert torch.equal(last3["out"].kpts, expect[-1][3]) and torch.equal(last3["out"].inlier_mask, expect[-1][1])
+    assert torch.equal(last3["out"].pose7, last["out"].pose7)

@@ -39,6 +39,11 @@ for _ in range(3):
     slot = pipe.submit(dhm, dc, ds)
 pipe.drain()
 torch.cuda.synchronize()
+pipe = StreamedHeatmapToPose(st, 48, depth=3, overlap_decode=True)  # background decode CTAs on their own stream
+for _ in range(4):
+    slot = pipe.submit(dhm, dc, ds)
+pipe.drain()
+torch.cuda.synchronize()
 # the Jacobi-SVD eigen stage (SPE_FLAG_JACOBI_SVD)
 kp = slot["out"].kpts.clone()
 st.solver.solve(kp, hypotheses=96, eig="jacobi")
