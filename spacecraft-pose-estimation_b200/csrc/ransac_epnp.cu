@@ -630,6 +630,7 @@ constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alp
 // shared memory of one warp: landmarks [32][3], ideal + raw pixels [32] float2 each, per-thread scratch
 constexpr int kT1WarpBytes = (int)(sizeof(float) * 3 * kMaxLandmarks + 2 * sizeof(float2) * kMaxLandmarks + sizeof(float) * 32 * kT1Stride +
                                    kMaxLandmarks /* landmark id of every compacted point */);
+constexpr int kT1MaxWarps = 12;  // 12 x 168 registers x 32 = one SM's register file
 static_assert(kT1WarpBytes % 16 == 0, "per-warp shared-memory slice must stay 16-byte aligned");
 
 // One Jacobi rotation between the columns at register positions P and Q of A, with the two
@@ -2057,11 +2058,13 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
       e = once.run(m.device, [] {
         cudaError_t r = cudaFuncSetAttribute(hypothesis_kernel_t1<0>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
         if (r == cudaSuccess) r = cudaFuncSetAttribute(hypothesis_kernel_t1<1>, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+        if (r == cudaSuccess) r = cudaFuncSetAttribute(hypothesis_kernel_t1<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT1MaxWarps * kT1WarpBytes);
+        if (r == cudaSuccess) r = cudaFuncSetAttribute(hypothesis_kernel_t1<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kT1MaxWarps * kT1WarpBytes);
         return r;
       });
       if (e != cudaSuccess) return e;
       const bool jacobi = a.kernel_variant == 2;  // full SVD of M^T (kept for A/B measurements)
-      const int kWarps = a.t1_warps >= 1 && a.t1_warps <= 4 ? a.t1_warps : 4;
+      const int kWarps = a.t1_warps >= 1 && a.t1_warps <= kT1MaxWarps ? a.t1_warps : kT1MaxWarps;
       const size_t smem = (size_t)kWarps * kT1WarpBytes;
       auto launch = [&](int h_begin, int h_count, const int32_t* need) -> cudaError_t {
         const int hblocks = (h_count + 31) / 32;
