@@ -71,7 +71,7 @@ __device__ __forceinline__ void jacobi_angle_fast(float a, float b, float p, flo
   // t = 2p / (h + sign(h) sqrt(h^2 + 4p^2)), h = b - a  ==  sign(zeta) / (|zeta| + sqrt(zeta^2 + 1)) with zeta = h / 2p,
   // in a 3-MUFU dependent chain (sqrt, rcp, rsqrt) instead of 4
   const float h = b - a, gg = p + p;
-  const float q = sqrt_approx(fmaf(h, h, gg * gg));
+  const float q = sqrt_approx(fmaf(h, h, fmaf(gg, gg, 1e-37f)));  // h = p = 0 -> t = 0
   t = gg * rcp_approx(h + copysignf(q, h));
   c = rsqrt_approx(fmaf(t, t, 1.0f));
   s = c * t;
@@ -469,11 +469,9 @@ __device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3],
         const float a = B[m][0][p] * B[m][0][p] + B[m][1][p] * B[m][1][p] + B[m][2][p] * B[m][2][p];
         const float b = B[m][0][q] * B[m][0][q] + B[m][1][q] * B[m][1][q] + B[m][2][q] * B[m][2][q];
         const float g = B[m][0][p] * B[m][0][q] + B[m][1][p] * B[m][1][q] + B[m][2][p] * B[m][2][q];
-        const bool rot = g * g > (Real<float>::eps * Real<float>::eps) * a * b;
+        // no "already orthogonal" test: a negligible g gives a negligible t (jacobi_angle_fast keeps 0/0 away)
         float t;
-        jacobi_angle_fast(a, b, rot ? g : 1.0f, c[m], s[m], t);
-        c[m] = rot ? c[m] : 1.0f;
-        s[m] = rot ? s[m] : 0.0f;
+        jacobi_angle_fast(a, b, g, c[m], s[m], t);
       }
 #pragma unroll
       for (int m = 0; m < NB; ++m)
