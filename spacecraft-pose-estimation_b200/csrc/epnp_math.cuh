@@ -448,16 +448,16 @@ __device__ __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3])
 // 12 times); interleaving NB of them gives the scheduler NB independent chains per thread.
 template <int NB>
 __device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3], float (&R)[NB][3][3]) {
-  float B[NB][3][3], V[NB][3][3];
+  // One-sided Jacobi on B = A V without accumulating V: the rotated columns are b_j = sigma_j u_j, and the right
+  // vectors follow afterwards as v_j = A^T b_j / sigma_j^2 for the two largest columns; the third is their cross
+  // product (V is a product of rotations, det +1), exactly as the third u is rebuilt from the other two.
+  float B[NB][3][3];
 #pragma unroll
   for (int m = 0; m < NB; ++m)
 #pragma unroll
     for (int i = 0; i < 3; ++i)
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        B[m][i][j] = A[m][i][j];
-        V[m][i][j] = i == j ? 1.0f : 0.0f;
-      }
+      for (int j = 0; j < 3; ++j) B[m][i][j] = A[m][i][j];
 #pragma unroll 1
   for (int sweep = 0; sweep < Real<float>::svd3_sweeps; ++sweep) {
 #pragma unroll
@@ -480,9 +480,6 @@ __device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3],
           const float x = B[m][r][p], y = B[m][r][q];
           B[m][r][p] = c[m] * x - s[m] * y;
           B[m][r][q] = s[m] * x + c[m] * y;
-          const float vx = V[m][r][p], vy = V[m][r][q];
-          V[m][r][p] = c[m] * vx - s[m] * vy;
-          V[m][r][q] = s[m] * vx + c[m] * vy;
         }
     }
   }
@@ -492,13 +489,20 @@ __device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3],
 #pragma unroll
     for (int j = 0; j < 3; ++j) n2[j] = B[m][0][j] * B[m][0][j] + B[m][1][j] * B[m][1][j] + B[m][2][j] * B[m][2][j];
     const int jmin = (n2[0] <= n2[1] && n2[0] <= n2[2]) ? 0 : (n2[1] <= n2[2] ? 1 : 2);
-    float U[3][3];
+    float U[3][3], V[3][3];  // V[c][j] = component c of v_j
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const float inv = rsqrt_approx(n2[j] > Real<float>::tiny ? n2[j] : 1.0f);
+      const bool ok = n2[j] > Real<float>::tiny;
+      const float inv = rsqrt_approx(ok ? n2[j] : 1.0f);
 #pragma unroll
       for (int r = 0; r < 3; ++r) U[r][j] = B[m][r][j] * inv;
+      // v_j = A^T u_j / sigma_j = A^T b_j / sigma_j^2;  inv2 * sigma_j = 1 / sigma_j^2
+      const float w = ok ? inv * inv : 0.0f;
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc)
+        V[cc][j] = (A[m][0][cc] * B[m][0][j] + A[m][1][cc] * B[m][1][j] + A[m][2][cc] * B[m][2][j]) * w;
     }
+    // rebuild column jmin of U and of V from the other two (cyclic order keeps the orientation bookkeeping simple)
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       if (j == jmin) {
@@ -511,12 +515,18 @@ __device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3],
         U[0][j] = sg * cx;
         U[1][j] = sg * cy;
         U[2][j] = sg * cz;
+        const float vx = V[1][j1] * V[2][j2] - V[2][j1] * V[1][j2];
+        const float vy = V[2][j1] * V[0][j2] - V[0][j1] * V[2][j2];
+        const float vz = V[0][j1] * V[1][j2] - V[1][j1] * V[0][j2];
+        V[0][j] = vx;
+        V[1][j] = vy;
+        V[2][j] = vz;
       }
     }
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) R[m][r][cc] = U[r][0] * V[m][cc][0] + U[r][1] * V[m][cc][1] + U[r][2] * V[m][cc][2];
+      for (int cc = 0; cc < 3; ++cc) R[m][r][cc] = U[r][0] * V[cc][0] + U[r][1] * V[cc][1] + U[r][2] * V[cc][2];
     const float det = R[m][0][0] * (R[m][1][1] * R[m][2][2] - R[m][1][2] * R[m][2][1]) -
                       R[m][0][1] * (R[m][1][0] * R[m][2][2] - R[m][1][2] * R[m][2][0]) +
                       R[m][0][2] * (R[m][1][0] * R[m][2][1] - R[m][1][1] * R[m][2][0]);
