@@ -40,7 +40,7 @@ WORKLOAD = "SPEED+ Tango 11 landmarks, 64x64 heatmaps, batch 4096 per GPU, 256 R
 # SURVEY §8(d) algorithmic work
 DECODE_BYTES_PER_FRAME = J * HM_H * HM_W * 4 + J * 12 + 16
 HYP_FLOPS = 126_400 + 54 * J  # canonical FP32 flops per hypothesis at n = J
-HYP_WARP_INSTR_PER_LAUNCH = 398_977_127 + 6_201_344  # ncu smsp__inst_executed.sum: hypothesis_kernel_t1 + frame_prep_kernel, 4096 frames x 256
+HYP_WARP_INSTR_PER_LAUNCH = 390_655_237 + 6_201_344  # ncu smsp__inst_executed.sum: hypothesis_kernel_t1 + frame_prep_kernel, 4096 frames x 256
 
 
 def config_dict(n_gpus):
