@@ -117,6 +117,14 @@ int spe_pnp_model_create(const double* landmarks, int J, const double* K, const 
                          int max_hypotheses, spe_model_t** out);
 int spe_pnp_model_destroy(spe_model_t* model);
 int spe_pnp_model_num_landmarks(const spe_model_t* model);
+/* Host-only (no CUDA call): one entry of the per-model control-point table that spe_pnp_model_create builds for every
+ * 5-subset of the landmarks and the hypothesis kernel looks up (EPnP's control points depend on the object points only,
+ * OpenCV epnp.cpp choose_control_points / compute_barycentric_coordinates).
+ * ids: five landmark indices in ascending order.  entry [20] float32: alpha[5][3] (barycentric coordinates with respect
+ * to the three PCA control points; the one of the centroid is 1 - their sum), then the three squared distances of those
+ * control points from the centroid, then two zeros.  rank (optional): position of the subset in the table. */
+int spe_pnp_control_entry(const double* landmarks, int J, const int32_t* ids, float* entry, int64_t* rank);
+
 /* copies the first `count` minimal sets for n points into out[count*5] (HOST), draw order kept */
 int spe_pnp_model_minimal_sets(const spe_model_t* model, int n, int count, int32_t* out);
 

@@ -158,6 +158,20 @@ int spe_pnp_model_minimal_sets(const spe_model_t* model, int n, int count, int32
   return SPE_OK;
 }
 
+int spe_pnp_control_entry(const double* landmarks, int J, const int32_t* ids, float* entry, int64_t* rank) {
+  if (landmarks == nullptr || ids == nullptr || entry == nullptr || J < 5 || J > SPE_MAX_LANDMARKS) return SPE_ERR_INVALID_ARGUMENT;
+  int sorted[5];
+  for (int k = 0; k < 5; ++k) {
+    if (ids[k] < 0 || ids[k] >= J || (k > 0 && ids[k] <= ids[k - 1])) return SPE_ERR_INVALID_ARGUMENT;  // ascending, distinct
+    sorted[k] = ids[k];
+  }
+  float lm[SPE_MAX_LANDMARKS * 3];
+  for (int i = 0; i < 3 * J; ++i) lm[i] = (float)landmarks[i];
+  spe::control_table_entry(lm, sorted, entry);
+  if (rank) *rank = (int64_t)spe::control_table_rank(sorted);
+  return SPE_OK;
+}
+
 size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypotheses) {
   if (model == nullptr || B < 0 || hypotheses < 1) return 0;
   return spe::ransac_workspace_bytes(model->m.J, B, hypotheses);

@@ -81,6 +81,10 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
 cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream);
 cudaError_t launch_debug_scores(const RansacWorkspace& ws, int B, int H, int32_t* counts, uint32_t* masks, cudaStream_t stream);
 
+// Host side of the control-point table (ransac_epnp.cu): one entry, and the rank of a sorted 5-subset.
+void control_table_entry(const float* landmarks_f32, const int (&ids)[5], float* entry /* [kCtrlEntryFloats] */);
+size_t control_table_rank(const int (&sorted_ids)[5]);
+
 // OpenCV's RANSAC RNG: minimal sets for `count` points, draw order preserved.
 void opencv_minimal_sets(int count, int num, uint8_t* out /* [num][5] */);
 

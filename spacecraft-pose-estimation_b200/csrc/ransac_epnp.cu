@@ -96,6 +96,43 @@ static void sym3_jacobi(double S[3][3], double V[3][3]) {
   }
 }
 
+// one table entry from the float32 landmark coordinates of the five points (ascending landmark order)
+void control_table_entry(const float* landmarks_f32, const int (&ids)[5], float* e) {
+  double P[5][3], c0[3] = {0, 0, 0};
+  for (int k = 0; k < 5; ++k)
+    for (int c = 0; c < 3; ++c) {
+      P[k][c] = (double)landmarks_f32[3 * ids[k] + c];
+      c0[c] += P[k][c] * 0.2;
+    }
+  double S[3][3] = {}, V[3][3];
+  for (int k = 0; k < 5; ++k)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) S[r][c] += (P[k][r] - c0[r]) * (P[k][c] - c0[c]);
+  sym3_jacobi(S, V);
+  for (int i = 0; i < kCtrlEntryFloats; ++i) e[i] = 0.f;
+  for (int i = 0; i < 3; ++i) {
+    const double lam = S[i][i] > 0.0 ? S[i][i] : 0.0;
+    const double ki = sqrt(lam * 0.2);
+    const double inv = ki > 1e-12 ? 1.0 / ki : 0.0;
+    for (int k = 0; k < 5; ++k) {
+      double proj = 0.0;
+      for (int c = 0; c < 3; ++c) proj += (P[k][c] - c0[c]) * V[c][i];
+      e[3 * k + i] = (float)(proj * inv);
+    }
+    e[15 + i] = (float)(ki * ki);
+  }
+}
+
+// rank of a sorted 5-subset in the table (the device computes the same expression, hypothesis_kernel_t1)
+size_t control_table_rank(const int (&j)[5]) {
+  auto c = [](size_t n, int k) {
+    size_t r = 1;
+    for (int i = 0; i < k; ++i) r = r * (n - i) / (i + 1);
+    return n >= (size_t)k ? r : 0;
+  };
+  return c(j[0], 1) + c(j[1], 2) + c(j[2], 3) + c(j[3], 4) + c(j[4], 5);
+}
+
 static void build_control_table(const Model& m, std::vector<float>& table) {
   const int J = m.J;
   size_t count = 0;
@@ -108,29 +145,7 @@ static void build_control_table(const Model& m, std::vector<float>& table) {
         for (int j1 = 1; j1 < j2; ++j1)
           for (int j0 = 0; j0 < j1; ++j0, ++rank) {
             const int ids[5] = {j0, j1, j2, j3, j4};
-            double P[5][3], c0[3] = {0, 0, 0};
-            for (int k = 0; k < 5; ++k)
-              for (int c = 0; c < 3; ++c) {
-                P[k][c] = (double)m.landmarks_f32[3 * ids[k] + c];
-                c0[c] += P[k][c] * 0.2;
-              }
-            double S[3][3] = {}, V[3][3];
-            for (int k = 0; k < 5; ++k)
-              for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) S[r][c] += (P[k][r] - c0[r]) * (P[k][c] - c0[c]);
-            sym3_jacobi(S, V);
-            float* e = table.data() + rank * kCtrlEntryFloats;
-            for (int i = 0; i < 3; ++i) {
-              const double lam = S[i][i] > 0.0 ? S[i][i] : 0.0;
-              const double ki = sqrt(lam * 0.2);
-              const double inv = ki > 1e-12 ? 1.0 / ki : 0.0;
-              for (int k = 0; k < 5; ++k) {
-                double proj = 0.0;
-                for (int c = 0; c < 3; ++c) proj += (P[k][c] - c0[c]) * V[c][i];
-                e[3 * k + i] = (float)(proj * inv);
-              }
-              e[15 + i] = (float)(ki * ki);
-            }
+            control_table_entry(m.landmarks_f32, ids, table.data() + rank * kCtrlEntryFloats);
           }
 }
 

@@ -58,6 +58,8 @@ def _declare(L):
         L.spe_pnp_model_num_landmarks.argtypes = [c_void_p]
         L.spe_pnp_model_minimal_sets.restype = c_int
         L.spe_pnp_model_minimal_sets.argtypes = [c_void_p, c_int, c_int, POINTER(c_int32)]
+        L.spe_pnp_control_entry.restype = c_int
+        L.spe_pnp_control_entry.argtypes = [POINTER(c_double), c_int, POINTER(c_int32), POINTER(c_float), POINTER(ctypes.c_int64)]
         L.spe_ransac_workspace_bytes.restype = c_size_t
         L.spe_ransac_workspace_bytes.argtypes = [c_void_p, c_int, c_int]
         L.spe_ransac_epnp_f32.restype = c_int
@@ -85,7 +87,7 @@ DECODE_BACKGROUND = 1
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",
     "spe_decode_kpts_f32", "spe_decode_kpts_ex_f32", "spe_decode_combined_kpts_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
-    "spe_pnp_model_minimal_sets", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_score_f32",
+    "spe_pnp_model_minimal_sets", "spe_pnp_control_entry", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_score_f32",
     "spe_ransac_select_refit_f32", "spe_ransac_debug_scores",
     "spe_pipeline_workspace_bytes", "spe_heatmap_to_pose_f32",
 )

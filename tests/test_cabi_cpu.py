@@ -97,3 +97,51 @@ def test_pose_entry_points_validate_arguments_without_gpu(lib):
     assert lib.spe_decode_combined_kpts_f32(ptrs, 3, 1, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # flip needs K == 2
     assert lib.spe_decode_combined_kpts_f32(ptrs, 2, 7, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # unknown mode
     assert lib.spe_decode_combined_kpts_f32(ptrs, 2, 0, None, 0, 0, 11, 64, 64, None, None, 1, None, None, None) == 0  # empty batch
+
+
+def test_control_point_table_entries_on_the_host(lib):
+    """spe_pnp_control_entry (host only): the per-subset control-point data the hypothesis kernel looks up.
+    The entry must reproduce the geometry of the five points — alphas are coordinates in an orthonormal PCA
+    frame scaled by k_i = sqrt(lambda_i / 5) (OpenCV epnp.cpp choose_control_points) — and the rank must walk
+    the table in the order model creation fills it."""
+    import ctypes
+    import itertools
+
+    rng = np.random.default_rng(5)
+    J = 9
+    lm = np.ascontiguousarray(rng.uniform(-1, 1, (J, 3)) * np.array([0.6, 0.5, 0.2]))
+    lm32 = lm.astype(np.float32).astype(np.float64)
+    dp = lm.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    ranks = []
+    for ids in itertools.combinations(range(J), 5):
+        idv = np.array(ids, np.int32)
+        entry = np.zeros(20, np.float32)
+        rank = ctypes.c_int64(-1)
+        rc = lib.spe_pnp_control_entry(dp, J, idv.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                       entry.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), ctypes.byref(rank))
+        assert rc == 0
+        ranks.append(rank.value)
+        al = entry[:15].reshape(5, 3).astype(np.float64)
+        ksq = entry[15:18].astype(np.float64)
+        assert np.all(entry[18:] == 0)
+        P = lm32[list(ids)]
+        # principal components: zero mean, orthogonal, variance 5 (unit-variance coordinates times k_i)
+        np.testing.assert_allclose(al.sum(0), 0, atol=2e-5)
+        np.testing.assert_allclose(al.T @ al, 5 * np.eye(3), atol=2e-4)
+        # k_i^2 = eigenvalues of the covariance / 5
+        lam = np.linalg.eigvalsh((P - P.mean(0)).T @ (P - P.mean(0))) / 5
+        np.testing.assert_allclose(np.sort(ksq), lam, rtol=2e-5, atol=1e-9)
+        # the alphas and k reproduce every pairwise distance of the five points
+        d_true = ((P[:, None] - P[None]) ** 2).sum(-1)
+        d_tab = (((al[:, None] - al[None]) ** 2) * ksq).sum(-1)
+        np.testing.assert_allclose(d_tab, d_true, rtol=2e-4, atol=1e-7)
+    # combinations in colexicographic order = 0 .. C(J,5)-1, each exactly once
+    assert sorted(ranks) == list(range(126))
+    colex = sorted(itertools.combinations(range(J), 5), key=lambda t: t[::-1])
+    assert [ranks[list(itertools.combinations(range(J), 5)).index(t)] for t in colex] == list(range(126))
+    # argument errors: unsorted / repeated / out-of-range ids
+    entry = np.zeros(20, np.float32)
+    for bad in ([0, 2, 1, 3, 4], [0, 1, 1, 3, 4], [0, 1, 2, 3, 9]):
+        idv = np.array(bad, np.int32)
+        assert lib.spe_pnp_control_entry(dp, J, idv.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                         entry.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), None) == -1
