@@ -25,6 +25,8 @@
 // Compute-bound on FP32 CUDA cores (no tensor cores: nothing here is a dense contraction);
 // HBM traffic is ~100 B per hypothesis.
 #include <cuda_runtime.h>
+
+#include <algorithm>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -2079,11 +2081,17 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
       });
       if (e != cudaSuccess) return e;
       const bool jacobi = a.kernel_variant == 2;  // full SVD of M^T (kept for A/B measurements)
-      const int kWarps = a.t1_warps >= 1 && a.t1_warps <= kT1MaxWarps ? a.t1_warps : kT1MaxWarps;
-      const size_t smem = (size_t)kWarps * kT1WarpBytes;
+      const int max_warps = a.t1_warps >= 1 && a.t1_warps <= kT1MaxWarps ? a.t1_warps : kT1MaxWarps;
+      int dev = 0, num_sms = 0;
+      e = current_device(dev, num_sms);
+      if (e != cudaSuccess) return e;
       auto launch = [&](int h_begin, int h_count, const int32_t* need) -> cudaError_t {
         const int hblocks = (h_count + 31) / 32;
-        const long long ctas = ((long long)a.B * hblocks + kWarps - 1) / kWarps;
+        // small batches: spread the warps over the SMs instead of packing 12 of them into one CTA
+        const long long items = (long long)a.B * hblocks;
+        const int kWarps = (int)std::min<long long>(max_warps, std::max<long long>(1, (items + num_sms - 1) / num_sms));
+        const size_t smem = (size_t)kWarps * kT1WarpBytes;
+        const long long ctas = (items + kWarps - 1) / kWarps;
         if (ctas > 0x7fffffffLL) return cudaErrorInvalidValue;
         if (ctas == 0) return cudaSuccess;
         if (jacobi)
