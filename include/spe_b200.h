@@ -10,6 +10,9 @@
  *   spe_ransac_epnp_f32      the per-frame loop   pose_estimation/export_predicted_poses_real.py:177-204
  *                            (confidence filter :186-197, cv2.solvePnPRansac :199-201,
  *                             cv2.Rodrigues :203, cv_rotation_matrix_to_quat :22-57)
+ *   spe_pick_boxes_f32 / spe_boxes_to_center_scale_f64
+ *                            detection box choice + _xywh2cs (object_detection/export_object_detection_bounding_boxes.py
+ *                            :313-329, landmark_regression/lib/dataset/PEdataset.py:98-113)
  *   spe_heatmap_to_pose_f32  the two above back to back with no host hop (the reference goes
  *                            through pred.mat: lib/dataset/PEdataset.py:121-123 ->
  *                            export_predicted_poses_real.py:172-173)
@@ -20,8 +23,10 @@
  *   - the caller owns every buffer; nothing is allocated per call (scratch comes from the
  *     caller-provided workspace, size from spe_ransac_workspace_bytes)
  *   - functions enqueue work on `stream` and return without synchronising; they are re-entrant
- *     and keep no global state; a model handle is immutable after creation and may be shared by
- *     threads using the same device
+ *     and keep no mutable global state (no environment variables are read, work counters live in
+ *     the caller's workspace and are zeroed on the call's stream); a model handle is immutable
+ *     after creation and may be shared by threads using the same device.  Calls that share a
+ *     workspace must be ordered by the caller (same stream, or events).
  *   - return value: SPE_OK (0) or a negative spe_status code; never throws across the ABI.
  *     Per-frame conditions are reported in status[b] (SPE_FRAME_*), not as errors.
  */
@@ -35,16 +40,17 @@
 extern "C" {
 #endif
 
-#define SPE_ABI_VERSION 1
+#define SPE_ABI_VERSION 2
 #define SPE_MAX_LANDMARKS 32 /* inlier masks are 32-bit */
-#define SPE_MAX_HYPOTHESES 4096
+#define SPE_MAX_HYPOTHESES 16384 /* >= the reference's iterationsCount = 10000 (export_predicted_poses_real.py:201) */
 
 typedef enum spe_status {
   SPE_OK = 0,
   SPE_ERR_INVALID_ARGUMENT = -1, /* null pointer, non-positive size, J > SPE_MAX_LANDMARKS ... */
   SPE_ERR_CUDA = -2,             /* a CUDA runtime call failed; see spe_last_cuda_error() */
   SPE_ERR_WORKSPACE = -3,        /* workspace too small or misaligned */
-  SPE_ERR_UNSUPPORTED = -4
+  SPE_ERR_UNSUPPORTED = -4,       /* a configuration outside the reference's (camera skew, development-only flags ...) */
+  SPE_ERR_OUT_OF_MEMORY = -5      /* host allocation failed while building a model */
 } spe_status;
 
 /* status[b] values written by spe_ransac_epnp_f32 (what cv2 would have done) */
@@ -108,11 +114,31 @@ int spe_decode_combined_kpts_f32(const float* const* srcs, int K, int mode, cons
                                  const float* scale, int post_process, float* kpts, int32_t* argmax,
                                  void* stream);
 
+/* ---- detection boxes -> (center, scale) -----------------------------------------
+ * spe_boxes_to_center_scale_f64   JointsDataset._xywh2cs, landmark_regression/lib/dataset/PEdataset.py:98-113
+ *                                 (pixel_std = 200, :41): xywh [B,4] float64 COCO boxes (the annotation's 'bbox') ->
+ *                                 center [B,2], scale [B,2] float32 = the meta['center'] / meta['scale'] the decode takes.
+ * spe_pick_boxes_f32              the per-image box choice of object_detection/export_object_detection_bounding_boxes.py
+ *                                 :313-329 followed by _xywh2cs: boxes [B,K,4] float32 (x1,y1,x2,y2), scores [B,K]
+ *                                 float32, counts [B] int32 = detections per image (NULL: K everywhere).  An image
+ *                                 with 1 or 2 detections keeps the best-scoring one (first maximum, a NaN wins), any
+ *                                 other count takes the whole image [0,0,image_w,image_h] with score 0.
+ *                                 Outputs (each may be NULL; center and scale only together): xywh [B,4] float64 (the
+ *                                 annotation's 'bbox'), best_score [B] float32, best_index [B] int32 (-1: whole image),
+ *                                 center/scale [B,2] float32. */
+int spe_boxes_to_center_scale_f64(const double* xywh, int B, float* center, float* scale, void* stream);
+int spe_pick_boxes_f32(const float* boxes, const float* scores, const int32_t* counts, int B, int K, double image_w,
+                       double image_h, double* xywh, float* best_score, int32_t* best_index, float* center,
+                       float* scale, void* stream);
+
 /* ---- pose ---------------------------------------------------------------------------------
  * landmarks [J,3] float64 HOST (metres; rounded to float32 internally exactly like cv2 does),
- * K[9] row-major float64 HOST, dist[5] = (k1,k2,p1,p2,k3) float64 HOST (NULL = no distortion).
- * max_hypotheses bounds `hypotheses` of later calls.  Builds the OpenCV-RNG minimal-set tables
- * for every point count 6..J on the current device. */
+ * K[9] row-major float64 HOST (pinhole without skew; anything else: SPE_ERR_UNSUPPORTED),
+ * dist[5] = (k1,k2,p1,p2,k3) float64 HOST (NULL = no distortion).
+ * max_hypotheses = cv2's iterationsCount (10000 in the reference, export_predicted_poses_real.py:201): it
+ * bounds `hypotheses` of later calls and is where the iteration budget of cv2's loop starts.  Builds, for every
+ * point count 6..J on the current device, the minimal sets OpenCV's fixed-seed RNG draws, the list of DISTINCT
+ * sets among them (a repeated 5-subset is scored once) and the control-point table of every 5-subset. */
 int spe_pnp_model_create(const double* landmarks, int J, const double* K, const double* dist,
                          int max_hypotheses, spe_model_t** out);
 int spe_pnp_model_destroy(spe_model_t* model);
@@ -125,24 +151,35 @@ int spe_pnp_model_num_landmarks(const spe_model_t* model);
  * control points from the centroid, then two zeros.  rank (optional): position of the subset in the table. */
 int spe_pnp_control_entry(const double* landmarks, int J, const int32_t* ids, float* entry, int64_t* rank);
 
+/* Host-only (no CUDA call, no model): the first `count` minimal sets OpenCV's RANSAC draws for n points (sets
+ * [count*5], draw order), the distinct-set number of every draw (slot [count]) and the draw that introduces each
+ * distinct set (uniq [count], -1 beyond *num_unique).  What spe_pnp_model_create uploads; any output may be NULL. */
+int spe_pnp_minimal_sets_host(int n, int count, int32_t* sets, int32_t* slot, int32_t* uniq, int32_t* num_unique);
+
 /* copies the first `count` minimal sets for n points into out[count*5] (HOST), draw order kept */
 int spe_pnp_model_minimal_sets(const spe_model_t* model, int n, int count, int32_t* out);
 
 size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypotheses);
 
 /* kpts        [B,J,3] float32   (x, y, conf) rows as stored in pred.mat
- * hypotheses  number of minimal sets scored per frame (cv2's iterationsCount capped to what the
- *             GPU evaluates; selection replays cv2's sequential adaptive termination)
+ * hypotheses  number of minimal sets scored per frame by the FP32 hypothesis kernel (every distinct set once);
+ *             may be 0 with SPE_FLAG_EXACT (no FP32 scoring at all)
  * reproj_err  15.0 in the reference; confidence 0.99 (cv2 default)
  * conf_floor  a landmark takes part iff conf > conf_floor; pass a negative value to run the
  *             reference's adaptive 0.95*0.8^k filter per frame (export_predicted_poses_real.py:186-197)
- * pose7       [B,7] float32 = (qw,qx,qy,qz,tx,ty,tz)
+ * pose7       [B,7] float32 = (qw,qx,qy,qz,tx,ty,tz).  float32 resolves a rotation to ~1e-3 deg (less near pi)
+ *             and a translation to 6e-8 relative: parity-grade consumers read `rt`
  * inlier_mask [B] uint32 over the J landmarks (bit j); status [B] int32 (spe_frame_status)
  * winner_hyp  [B] int32 index of the accepted hypothesis (-1 none); may be NULL
  * rt          [B,12] float64 = row-major R (9) then t (3) of the final refit; may be NULL
- * flags       0, or SPE_FLAG_REFINE_LM: after the final EPnP, minimise the reprojection error over the
- *             inliers (the counterpart of cv2.solvePnPRefineLM; NOT part of the reference's call, whose
- *             SOLVEPNP_EPNP path ends with EPnP on the inliers — off by default everywhere)
+ *
+ * Which hypothesis wins (flags):
+ *   default         cv2's sequential acceptance rule replayed over the FP32 inlier counts of the first `hypotheses`
+ *                   draws.  Equals cv2's result whenever FP32 and cv2's float64 agree on the hypotheses cv2 looks at
+ *                   and cv2 stops within `hypotheses` draws; spe_ransac_read_budget tells when it would not have.
+ *   SPE_FLAG_EXACT  cv2's loop itself, replayed in float64 up to the model's max_hypotheses (iterationsCount):
+ *                   the hypotheses cv2 looks at (6.5 per frame on the benchmark data) are re-evaluated in float64,
+ *                   whatever the FP32 scores say.  This is the parity path.
  */
 #define SPE_FLAG_REFINE_LM 1
 /* SPE_FLAG_ADAPTIVE: score the first 32 minimal sets of every frame, replay cv2's acceptance loop
@@ -151,14 +188,15 @@ size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypothese
  * entries); the work is what cv2 itself would do, rounded up to blocks of 32.  Off by default. */
 #define SPE_FLAG_ADAPTIVE 2
 /* SPE_FLAG_BACKGROUND_TAIL (spe_ransac_select_refit_f32): the caller overlaps this call with the
- * scoring of the next batch on another stream; the refit then keeps its working matrix in local
- * instead of shared memory so that it fits next to the hypothesis kernel's CTAs. */
+ * scoring of the next batch on another stream; the refit is then launched as whole-SM CTAs on few
+ * SMs instead of one warp on every SM. */
 #define SPE_FLAG_BACKGROUND_TAIL 4
 /* SPE_FLAG_JACOBI_SVD (scoring): take EPnP's four vectors from a full one-sided Jacobi SVD of M^T
  * (the reference algorithm's eigensolve, 2.3x slower) instead of the default Householder QR + block
- * inverse iteration.  Same results up to the chaos of near-degenerate hypotheses; kept for A/B
- * measurements and for the test that compares the two (tests/test_pnp_gpu.py). */
-#define SPE_FLAG_JACOBI_SVD 8
+ * inverse iteration.  Same results up to the chaos of near-degenerate hypotheses; a development variant
+ * for A/B measurements (tests/test_pnp_gpu.py compares the two when the library was built with it). */
+#define SPE_FLAG_JACOBI_SVD 8 /* development builds (-DSPE_DEV) only; SPE_ERR_UNSUPPORTED otherwise */
+#define SPE_FLAG_EXACT 16
 int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses,
                         float reproj_err, double confidence, float conf_floor, float* pose7,
                         uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
@@ -177,8 +215,20 @@ int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses,
                                 int32_t* winner_hyp, double* rt, void* workspace,
                                 size_t workspace_bytes, int flags, void* stream);
 
-/* Per-hypothesis scores of the most recent spe_ransac_epnp_f32 call on this workspace, for the
- * parity tests: counts [B,hypotheses] int32 and masks [B,hypotheses] uint32 (DEVICE). */
+/* SPE_FLAG_EXACT as its own stage, between spe_ransac_score_f32 and spe_ransac_select_refit_f32 (which must then be
+ * given SPE_FLAG_EXACT too): the float64 replay of cv2's loop for every frame of the workspace.  It needs the frame
+ * preparation of spe_ransac_score_f32 (which may have been called with hypotheses = 0) and the same B / hypotheses. */
+int spe_ransac_replay_f64(const spe_model_t* model, int B, int hypotheses, float reproj_err, double confidence,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* budget [B] int32 DEVICE, valid after spe_ransac_select_refit_f32 / spe_ransac_epnp_f32 on this workspace: cv2's
+ * iteration budget when its loop ends = the number of hypotheses it looks at.  Without SPE_FLAG_EXACT a value above
+ * `hypotheses` means cv2 would have kept drawing beyond what was scored (re-run those frames with SPE_FLAG_EXACT). */
+int spe_ransac_read_budget(const spe_model_t* model, const void* workspace, int B, int hypotheses, int32_t* budget,
+                           void* stream);
+
+/* Per-hypothesis FP32 scores of the most recent spe_ransac_epnp_f32 call on this workspace, for the
+ * parity tests: counts [B,hypotheses] int32 and masks [B,hypotheses] uint32 (DEVICE), in draw order. */
 int spe_ransac_debug_scores(const spe_model_t* model, const void* workspace, int B, int hypotheses,
                             int32_t* counts, uint32_t* masks, void* stream);
 

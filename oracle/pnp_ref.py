@@ -189,3 +189,61 @@ def pose_errors(pose_a: np.ndarray, pose_b: np.ndarray):
     ra, rb = quat_to_matrix(pose_a[:4]), quat_to_matrix(pose_b[:4])
     ta, tb = np.asarray(pose_a[4:], np.float64), np.asarray(pose_b[4:], np.float64)
     return rotation_angle_deg(ra, rb), float(np.linalg.norm(ta - tb) / max(np.linalg.norm(tb), 1e-30))
+
+
+# ----------------------------------------------------------------------------- float64 white box without cv2
+def ransac_epnp_numpy(obj, img, K, dist, iterations=ITERATIONS_COUNT, reproj=REPROJECTION_ERROR, confidence=CONFIDENCE):
+    """cv2.solvePnPRansac(EPNP) restated end to end in NumPy float64 — OpenCV's RNG and loop (ocv_rng), this package's
+    own EPnP (epnp_ref, incl. the port of OpenCV's Jacobi SVD), undistortion and projection; no cv2 call.  It is the
+    "float64 white box" of the parity tests: an independent float64 implementation of the same algorithm.  Where it
+    and cv2 disagree on a frame's inlier set, the frame's answer depends on rounding noise (the 2-D null space of
+    5-point EPnP).  Returns (ok, R, t, inlier indices or None, winner, hypotheses looked at)."""
+    from . import epnp_ref
+
+    obj32 = np.ascontiguousarray(obj, np.float32)
+    img32 = np.ascontiguousarray(img, np.float32)
+    n = obj32.shape[0]
+    if n < 6:
+        raise ValueError("the white box covers the RANSAC branch (n >= 6)")
+    thr = np.float32(reproj * reproj)
+    und32 = epnp_ref.undistort_points(img32, K, dist)  # float32 out, as cv2 does for float32 input
+    niters, best, max_good, h, best_good = int(iterations), -1, 0, 0, None
+    subsets = ocv_rng.minimal_sets(n, min(int(iterations), 64))
+    while h < niters:
+        if h >= len(subsets):
+            subsets = ocv_rng.minimal_sets(n, min(int(iterations), len(subsets) * 4))
+        s = subsets[h]
+        R, t = epnp_ref.epnp(obj32[s].astype(np.float64), und32[s].astype(np.float64), K)
+        proj = epnp_ref.project_points(obj32.astype(np.float64), R, t, K, dist).astype(np.float32)
+        d = img32 - proj
+        with np.errstate(over="ignore", invalid="ignore"):
+            good = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) <= thr
+        c = int(good.sum())
+        if c > max(max_good, 4):
+            best, max_good, best_good = h, c, good.copy()
+            niters = ocv_rng.update_num_iters(confidence, (n - c) / n, 5, niters)
+        h += 1
+    if best < 0:
+        return False, None, None, None, -1, h
+    inl = np.flatnonzero(best_good).astype(np.int32)
+    und64 = epnp_ref.undistort_points(img32[inl].astype(np.float64), K, dist)
+    R, t = epnp_ref.epnp(obj32[inl].astype(np.float64), und64, K)
+    return True, R, t, inl, best, h
+
+
+def cv2_is_unstable(obj, img, K, dist, trials: int = 8, seed: int = 0, iterations=ITERATIONS_COUNT, reproj=REPROJECTION_ERROR):
+    """Does cv2.solvePnPRansac itself return a different inlier set when every image coordinate is moved by at most one
+    float32 ulp (~1e-4 px: nothing a measurement could resolve)?  Then the frame's answer is decided by rounding noise
+    inside OpenCV, not by the data: no second implementation — nor cv2 on another CPU — can be expected to reproduce it."""
+    img32 = np.ascontiguousarray(img, np.float32)
+    ok0, _, _, inl0 = solve_pnp_ransac_cv2(obj, img32, K, dist, iterations, reproj)
+    ref = None if inl0 is None else tuple(int(i) for i in inl0)
+    rng = np.random.default_rng(seed)
+    for _ in range(trials):
+        step = rng.integers(-1, 2, img32.shape)
+        p = np.where(step > 0, np.nextafter(img32, np.float32(np.inf)), np.where(step < 0, np.nextafter(img32, np.float32(-np.inf)), img32))
+        ok, _, _, inl = solve_pnp_ransac_cv2(obj, p.astype(np.float32), K, dist, iterations, reproj)
+        got = None if inl is None else tuple(int(i) for i in inl)
+        if ok != ok0 or got != ref:
+            return True
+    return False

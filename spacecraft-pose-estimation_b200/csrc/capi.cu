@@ -3,10 +3,12 @@
 #include <stdlib.h>
 
 #include "../../include/spe_b200.h"
+#include "boxes.cuh"
 #include "decode.cuh"
 #include "ransac.cuh"
 
 #include <new>
+#include <stdexcept>
 
 namespace {
 
@@ -56,6 +58,7 @@ const char* spe_status_string(int status) {
     case SPE_ERR_CUDA: return "CUDA runtime error";
     case SPE_ERR_WORKSPACE: return "workspace too small or misaligned";
     case SPE_ERR_UNSUPPORTED: return "unsupported configuration";
+    case SPE_ERR_OUT_OF_MEMORY: return "out of host memory";
     default: return "unknown status";
   }
 }
@@ -113,6 +116,27 @@ int spe_decode_combined_kpts_f32(const float* const* srcs, int K, int mode, cons
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
 
+// ---- detection boxes -> (center, scale) --------------------------------------------------------
+int spe_boxes_to_center_scale_f64(const double* xywh, int B, float* center, float* scale, void* stream) {
+  if (B < 0) return SPE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SPE_OK;
+  if (xywh == nullptr || center == nullptr || scale == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  const cudaError_t e = spe::launch_xywh2cs(xywh, B, center, scale, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
+int spe_pick_boxes_f32(const float* boxes, const float* scores, const int32_t* counts, int B, int K, double image_w, double image_h, double* xywh,
+                       float* best_score, int32_t* best_index, float* center, float* scale, void* stream) {
+  if (B < 0 || K < 0) return SPE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SPE_OK;
+  if ((center == nullptr) != (scale == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
+  if (K > 0 && (boxes == nullptr || scores == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
+  if (K == 0 && counts != nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  const cudaError_t e = spe::launch_pick_boxes(boxes, scores, counts, B, K, image_w, image_h, xywh, best_score, best_index, center, scale,
+                                               static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
 // ---- pose ----------------------------------------------------------------------------------
 struct spe_model {
   spe::Model m;
@@ -123,8 +147,10 @@ int spe_pnp_model_create(const double* landmarks, int J, const double* K, const 
   *out = nullptr;
   if (landmarks == nullptr || K == nullptr || J < 4 || J > SPE_MAX_LANDMARKS) return SPE_ERR_INVALID_ARGUMENT;
   if (max_hypotheses < 1 || max_hypotheses > SPE_MAX_HYPOTHESES) return SPE_ERR_INVALID_ARGUMENT;
+  // the pinhole + (k1,k2,p1,p2,k3) model the reference's calibration.json holds: no skew, a plain last row
+  if (K[1] != 0.0 || K[3] != 0.0 || K[6] != 0.0 || K[7] != 0.0 || K[8] != 1.0 || !(K[0] > 0.0) || !(K[4] > 0.0)) return SPE_ERR_UNSUPPORTED;
   spe_model* h = new (std::nothrow) spe_model();
-  if (h == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  if (h == nullptr) return SPE_ERR_OUT_OF_MEMORY;
   spe::Model& m = h->m;
   m.J = J;
   m.max_hyp = max_hypotheses;
@@ -132,7 +158,18 @@ int spe_pnp_model_create(const double* landmarks, int J, const double* K, const 
   m.cam.fx = K[0], m.cam.cx = K[2], m.cam.fy = K[4], m.cam.cy = K[5];
   m.cam.k1 = dist ? dist[0] : 0.0, m.cam.k2 = dist ? dist[1] : 0.0, m.cam.p1 = dist ? dist[2] : 0.0;
   m.cam.p2 = dist ? dist[3] : 0.0, m.cam.k3 = dist ? dist[4] : 0.0;
-  const cudaError_t e = spe::model_upload(m);
+  cudaError_t e = cudaSuccess;
+  try {  // the tables are std::vectors (the control-point table alone is 16 MB for J = 32): nothing may throw across the ABI
+    e = spe::model_upload(m);
+  } catch (const std::bad_alloc&) {
+    spe::model_free(m);
+    delete h;
+    return SPE_ERR_OUT_OF_MEMORY;
+  } catch (...) {
+    spe::model_free(m);
+    delete h;
+    return SPE_ERR_UNSUPPORTED;
+  }
   if (e != cudaSuccess) {
     spe::model_free(m);
     delete h;
@@ -158,6 +195,26 @@ int spe_pnp_model_minimal_sets(const spe_model_t* model, int n, int count, int32
   return SPE_OK;
 }
 
+int spe_pnp_minimal_sets_host(int n, int count, int32_t* sets, int32_t* slot, int32_t* uniq, int32_t* num_unique) {
+  if (n < 6 || n > SPE_MAX_LANDMARKS || count < 1 || count > SPE_MAX_HYPOTHESES) return SPE_ERR_INVALID_ARGUMENT;
+  try {
+    std::vector<uint8_t> sub((size_t)count * spe::kModelPoints);
+    std::vector<uint16_t> u(count), s(count);
+    spe::opencv_minimal_sets(n, count, sub.data());
+    const int nu = spe::build_unique(sub.data(), count, u.data(), s.data());
+    for (int i = 0; i < count; ++i) {
+      if (sets)
+        for (int k = 0; k < spe::kModelPoints; ++k) sets[i * spe::kModelPoints + k] = sub[(size_t)i * spe::kModelPoints + k];
+      if (slot) slot[i] = s[i];
+      if (uniq) uniq[i] = i < nu ? (int32_t)u[i] : -1;
+    }
+    if (num_unique) *num_unique = nu;
+  } catch (...) {
+    return SPE_ERR_OUT_OF_MEMORY;
+  }
+  return SPE_OK;
+}
+
 int spe_pnp_control_entry(const double* landmarks, int J, const int32_t* ids, float* entry, int64_t* rank) {
   if (landmarks == nullptr || ids == nullptr || entry == nullptr || J < 5 || J > SPE_MAX_LANDMARKS) return SPE_ERR_INVALID_ARGUMENT;
   int sorted[5];
@@ -172,53 +229,36 @@ int spe_pnp_control_entry(const double* landmarks, int J, const int32_t* ids, fl
   return SPE_OK;
 }
 
-size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypotheses) {
-  if (model == nullptr || B < 0 || hypotheses < 1) return 0;
-  return spe::ransac_workspace_bytes(model->m.J, B, hypotheses);
+#ifdef SPE_DEV
+// Development builds only (-DSPE_DEV): environment knobs for A/B runs.  The shipped library reads no environment
+// variables and keeps no mutable global state.
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
 }
-
-static int hyp_kernel_setting() {
-  static int variant = [] {
-    // dev knob for A/B runs: "g4" = 4 lanes per hypothesis, "jacobi" = thread per hypothesis with the full
-    // one-sided Jacobi SVD of M^T; default = thread per hypothesis, Householder QR + inverse iteration
-    const char* v = getenv("SPE_HYP_KERNEL");
+static void dev_knobs(spe::RansacArgs& a) {
+  static const int variant = [] {
+    const char* v = getenv("SPE_HYP_KERNEL");  // "g4" = 4 lanes per hypothesis, "jacobi" = full one-sided Jacobi SVD of M^T
     return (v && v[0] == 'g') ? 1 : (v && v[0] == 'j') ? 2 : 0;
   }();
-  return variant;
+  static const int iters = env_int(variant == 0 ? "SPE_EIG_ITERS" : "SPE_JACOBI_SWEEPS", variant == 1 ? 5 : 6);
+  static const int t1_warps = env_int("SPE_T1_WARPS", 0), tail_warps = env_int("SPE_TAIL_WARPS", 0);
+  a.kernel_variant = variant;
+  a.eig_iters = iters > 0 && iters <= 30 ? iters : 6;
+  a.t1_warps = t1_warps;
+  a.tail_warps = tail_warps;
 }
+#endif
 
-static int jacobi_sweeps_setting() {
-  static int sweeps = [] {
-    // dev knob: Jacobi sweeps (variants 1, 2) or inverse-iteration steps (variant 0)
-    const char* v = getenv(hyp_kernel_setting() == 0 ? "SPE_EIG_ITERS" : "SPE_JACOBI_SWEEPS");
-    const int dflt = hyp_kernel_setting() == 1 ? 5 : 6;
-    const int s = v ? atoi(v) : dflt;
-    return s > 0 && s <= 30 ? s : dflt;
-  }();
-  return sweeps;
-}
-
-static int t1_warps_setting() {
-  static int warps = [] {
-    const char* v = getenv("SPE_T1_WARPS");  // dev knob: warps per CTA of the hypothesis kernel
-    const int w = v ? atoi(v) : 12;  // 12 warps x 168 registers = one CTA per SM: 0.673 vs 0.681 ms per pipelined step (4 warps)
-    return w >= 1 && w <= 12 ? w : 12;
-  }();
-  return warps;
-}
-
-static int tail_warps_setting() {
-  static int warps = [] {
-    const char* v = getenv("SPE_TAIL_WARPS");  // dev knob: warps per CTA of the background select/refit kernel
-    const int w = v ? atoi(v) : 0;  // 0: as many as fit one SM
-    return w >= 1 && w <= 32 ? w : 0;
-  }();
-  return warps;
-}
-
-static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, void* workspace, size_t workspace_bytes, spe::RansacArgs& a,
+static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, void* workspace, size_t workspace_bytes, int flags, spe::RansacArgs& a,
                             spe::RansacWorkspace& ws) {
-  if (model == nullptr || B < 0 || hypotheses < 1 || hypotheses > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
+  if (model == nullptr || B < 0 || hypotheses < 0 || hypotheses > model->m.max_hyp) return SPE_ERR_INVALID_ARGUMENT;
+  if (hypotheses == 0 && !(flags & SPE_FLAG_EXACT)) return SPE_ERR_INVALID_ARGUMENT;  // nothing to select from
+  if ((flags & SPE_FLAG_JACOBI_SVD)) {
+#ifndef SPE_DEV
+    return SPE_ERR_UNSUPPORTED;  // development variant, not in the shipped library
+#endif
+  }
   if (B > 0) {  // the model's tables live on the device it was created on
     int dev = -1;
     const cudaError_t e = cudaGetDevice(&dev);
@@ -230,19 +270,30 @@ static int fill_ransac_args(const spe_model_t* model, int B, int hypotheses, voi
   a = spe::RansacArgs{};
   a.B = B;
   a.H = hypotheses;
-  a.jacobi_sweeps = jacobi_sweeps_setting();
-  a.kernel_variant = hyp_kernel_setting();
-  a.t1_warps = t1_warps_setting();
-  a.tail_warps = tail_warps_setting();
+  a.iterations = model->m.max_hyp;  // cv2's iterationsCount
+  a.eig_iters = 6;
+  a.exact = (flags & SPE_FLAG_EXACT) ? 1 : 0;
+#ifdef SPE_DEV
+  dev_knobs(a);
+  if ((flags & SPE_FLAG_JACOBI_SVD) && a.kernel_variant == 0) {
+    a.kernel_variant = 2;
+    a.eig_iters = 6;
+  }
+#endif
   ws = spe::carve_workspace(workspace, model->m.J, B, hypotheses);
   return SPE_OK;
+}
+
+size_t spe_ransac_workspace_bytes(const spe_model_t* model, int B, int hypotheses) {
+  if (model == nullptr || B < 0 || hypotheses < 0) return 0;
+  return spe::ransac_workspace_bytes(model->m.J, B, hypotheses);
 }
 
 int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int hypotheses, float reproj_err, double confidence,
                          float conf_floor, void* workspace, size_t workspace_bytes, int flags, void* stream) {
   spe::RansacArgs a;
   spe::RansacWorkspace ws;
-  const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, a, ws);
+  const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, flags, a, ws);
   if (rc != SPE_OK || B == 0) return rc;
   if (kpts == nullptr || !(reproj_err > 0.f)) return SPE_ERR_INVALID_ARGUMENT;
   a.kpts = kpts;
@@ -250,11 +301,20 @@ int spe_ransac_score_f32(const spe_model_t* model, const float* kpts, int B, int
   a.confidence = confidence;
   a.conf_floor = conf_floor;
   a.adaptive = (flags & SPE_FLAG_ADAPTIVE) ? 1 : 0;
-  if ((flags & SPE_FLAG_JACOBI_SVD) && a.kernel_variant == 0) {
-    a.kernel_variant = 2;
-    a.jacobi_sweeps = 6;
-  }
   const cudaError_t e = spe::launch_ransac_score(model->m, a, ws, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
+int spe_ransac_replay_f64(const spe_model_t* model, int B, int hypotheses, float reproj_err, double confidence, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  spe::RansacArgs a;
+  spe::RansacWorkspace ws;
+  const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, SPE_FLAG_EXACT, a, ws);
+  if (rc != SPE_OK || B == 0) return rc;
+  if (!(reproj_err > 0.f)) return SPE_ERR_INVALID_ARGUMENT;
+  a.reproj_err = reproj_err;
+  a.confidence = confidence;
+  const cudaError_t e = spe::launch_ransac_replay(model->m, a, ws, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
 
@@ -263,7 +323,7 @@ int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses,
                                 void* stream) {
   spe::RansacArgs a;
   spe::RansacWorkspace ws;
-  const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, a, ws);
+  const int rc = fill_ransac_args(model, B, hypotheses, workspace, workspace_bytes, flags, a, ws);
   if (rc != SPE_OK || B == 0) return rc;
   if (pose7 == nullptr || inlier_mask == nullptr || status == nullptr) return SPE_ERR_INVALID_ARGUMENT;
   a.confidence = confidence;
@@ -272,6 +332,7 @@ int spe_ransac_select_refit_f32(const spe_model_t* model, int B, int hypotheses,
   a.status = status;
   a.winner = winner_hyp;
   a.rt = rt;
+  a.budget = ws.x_visited;  // kept in the workspace for spe_ransac_read_budget
   a.refine_lm = (flags & SPE_FLAG_REFINE_LM) ? 1 : 0;
   a.refit_background = (flags & SPE_FLAG_BACKGROUND_TAIL) ? 1 : 0;
   const cudaError_t e = spe::launch_ransac_select_refit(model->m, a, ws, static_cast<cudaStream_t>(stream));
@@ -282,22 +343,34 @@ int spe_ransac_epnp_f32(const spe_model_t* model, const float* kpts, int B, int 
                         float conf_floor, float* pose7, uint32_t* inlier_mask, int32_t* status, int32_t* winner_hyp, double* rt,
                         void* workspace, size_t workspace_bytes, int flags, void* stream) {
   if (B > 0 && (pose7 == nullptr || inlier_mask == nullptr || status == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
-  const int rc = spe_ransac_score_f32(model, kpts, B, hypotheses, reproj_err, confidence, conf_floor, workspace, workspace_bytes, flags, stream);
+  int rc = spe_ransac_score_f32(model, kpts, B, hypotheses, reproj_err, confidence, conf_floor, workspace, workspace_bytes, flags, stream);
   if (rc != SPE_OK) return rc;
+  if (flags & SPE_FLAG_EXACT) {
+    rc = spe_ransac_replay_f64(model, B, hypotheses, reproj_err, confidence, workspace, workspace_bytes, stream);
+    if (rc != SPE_OK) return rc;
+  }
   return spe_ransac_select_refit_f32(model, B, hypotheses, confidence, pose7, inlier_mask, status, winner_hyp, rt, workspace, workspace_bytes,
                                      flags, stream);
+}
+
+int spe_ransac_read_budget(const spe_model_t* model, const void* workspace, int B, int hypotheses, int32_t* budget, void* stream) {
+  if (model == nullptr || workspace == nullptr || budget == nullptr || B < 0 || hypotheses < 0) return SPE_ERR_INVALID_ARGUMENT;
+  if (B == 0) return SPE_OK;
+  const spe::RansacWorkspace ws = spe::carve_workspace(const_cast<void*>(workspace), model->m.J, B, hypotheses);
+  const cudaError_t e = cudaMemcpyAsync(budget, ws.x_visited, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
 
 int spe_ransac_debug_scores(const spe_model_t* model, const void* workspace, int B, int hypotheses, int32_t* counts, uint32_t* masks,
                             void* stream) {
   if (model == nullptr || workspace == nullptr || B < 0 || hypotheses < 1) return SPE_ERR_INVALID_ARGUMENT;
   const spe::RansacWorkspace ws = spe::carve_workspace(const_cast<void*>(workspace), model->m.J, B, hypotheses);
-  const cudaError_t e = spe::launch_debug_scores(ws, B, hypotheses, counts, masks, static_cast<cudaStream_t>(stream));
+  const cudaError_t e = spe::launch_debug_scores(model->m, ws, B, hypotheses, counts, masks, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
 
 size_t spe_pipeline_workspace_bytes(const spe_model_t* model, int B, int J, int hypotheses) {
-  if (model == nullptr || B < 0 || hypotheses < 1 || J != model->m.J) return 0;
+  if (model == nullptr || B < 0 || hypotheses < 0 || J != model->m.J) return 0;
   const size_t kp = ((size_t)B * J * 3 * sizeof(float) + 15) & ~(size_t)15;
   return kp + spe::ransac_workspace_bytes(J, B, hypotheses);
 }

@@ -40,6 +40,7 @@ struct Real<float> {
   static __device__ __forceinline__ float copysign(float m, float s) { return copysignf(m, s); }
   static constexpr float eps = 1.1920929e-7f;
   static constexpr float tiny = 1e-30f;
+  static constexpr float pivot_floor = 1e-7f;  // relative size below which a QR pivot counts as zero
   static constexpr int svd3_sweeps = 4;  // converged to rounding in 4 (200k random FP32 cases, worst |dR| 2.6e-6)
 };
 template <>
@@ -52,6 +53,7 @@ struct Real<double> {
   static __device__ __forceinline__ double copysign(double m, double s) { return ::copysign(m, s); }
   static constexpr double eps = 2.220446049250313e-16;
   static constexpr double tiny = 1e-280;
+  static constexpr double pivot_floor = 1e-15;
   static constexpr int svd3_sweeps = 8;
 };
 
@@ -535,6 +537,184 @@ __device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3],
       R[m][2][1] = -R[m][2][1];
       R[m][2][2] = -R[m][2][2];
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// EPnP's four vectors without a full SVD (a one-sided Jacobi SVD of M^T is kept as a development variant,
+// dev_variants.cuh).  EPnP needs the four smallest right singular directions of
+// the 10 x 12 matrix M only:
+//   * v0, v1 span the exact null space.  Householder QR of A = M^T (12 x 10, in place: R in the upper
+//     triangle, the reflectors below it) gives it for free: the last two columns of Q;
+//   * v2, v3 belong to the two smallest singular values of R (M^T M = Q R R^T Q^T): block inverse
+//     iteration x <- R^-T R^-1 x on two vectors (two triangular solves each, Gram-Schmidt every
+//     step), a 2 x 2 Rayleigh-Ritz rotation to separate them, then v = Q [w; 0; 0].
+// The bottom of M's spectrum is strongly graded for a perspective camera metres away from a
+// sub-metre target (sigma_2 / sigma_3 ~ 0.15 median on the benchmark data), so the iteration reaches
+// FP32 noise in 4-6 steps; where it has not (close range, sigma_3 ~ sigma_4) v3 is a mixture inside an
+// almost degenerate pair, which is as arbitrary in OpenCV's own SVD.  Checked against cv2 with the
+// NumPy model tools/proto_eig.py before it was written and on the GPU afterwards: per-hypothesis
+// inlier-count agreement and winner-mask agreement are the same as with the Jacobi SVD.
+// ~3.7 k instead of ~18 k instructions per hypothesis for this stage.
+// Row/column order of A = M^T in this routine (eig_row / the fill in the kernel): columns 0..4 are the
+// x-equations of the five points, 5..9 their y-equations; rows 0..7 are the (x, z) components of the
+// four control points, rows 8..11 the y components.  An x-equation has no y component, so the first
+// five reflectors and the columns they come from live in rows 0..7 only: every inner loop of steps
+// 0..4 (and of their later applications) stops at row 8 instead of 12 (kQrRowEnd).
+__device__ __forceinline__ constexpr int kQrRowEnd(int k) { return k < 5 ? 8 : 12; }
+// position in the 12-vector (control point j, component c) <- row of A
+__device__ __forceinline__ constexpr int eig_row_to_coord(int r) { return r < 8 ? 3 * (r / 2) + ((r & 1) ? 2 : 0) : 3 * (r - 8) + 1; }
+
+// T = float: the FP32 hypothesis kernel (SFU approximations, `work` in shared memory); T = double: the float64
+// replay (ransac_exact.cu).
+template <typename T>
+__device__ __forceinline__ void eig_qr_inverse_iteration(T (&A)[12][10], T* __restrict__ work, int iters) {
+  using R_ = Real<T>;
+  constexpr T kTiny = T(1e-30), kTinier = T(1e-37);
+  // ---- Householder QR, H_k = I - tau_k v_k v_k^T with v_k = (1, A[k+1..][k]) --------------------
+  // tau_k is parked in work[24 + k] (the v2 slot is free until the very end).
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    T ss = T(0);
+#pragma unroll
+    for (int i = k + 1; i < kQrRowEnd(k); ++i) ss = fma(A[i][k], A[i][k], ss);
+    const T x0 = A[k][k];
+    const T nn = fma(x0, x0, ss);
+    const bool ok = nn > kTiny;
+    const T nrm = R_::sqrt(nn);
+    const T v0 = x0 + R_::copysign(nrm, x0);
+    const T iv0 = ok ? R_::rcp(v0) : T(0);
+    const T tau = ok ? (R_::abs(x0) + nrm) * R_::rcp(nrm) : T(0);
+    work[24 + k] = tau;
+    A[k][k] = -R_::copysign(nrm, x0);
+#pragma unroll
+    for (int i = k + 1; i < kQrRowEnd(k); ++i) A[i][k] *= iv0;
+#pragma unroll
+    for (int j = k + 1; j < 10; ++j) {
+      T s = A[k][j];
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) s = fma(A[i][k], A[i][j], s);
+      s *= tau;
+      A[k][j] -= s;
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) A[i][j] = fma(-s, A[i][k], A[i][j]);
+    }
+  }
+  // y <- Q y = H_0 ( ... (H_9 y))
+  auto apply_q = [&](T (&y)[12]) {
+#pragma unroll
+    for (int k = 9; k >= 0; --k) {
+      T s = y[k];
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) s = fma(A[i][k], y[i], s);
+      s *= work[24 + k];
+      y[k] -= s;
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) y[i] = fma(-s, A[i][k], y[i]);
+    }
+  };
+  // ---- null space: the last two columns of Q ---------------------------------------------------
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    T y[12];
+#pragma unroll
+    for (int r = 0; r < 12; ++r) y[r] = r == 10 + c ? T(1) : T(0);
+    apply_q(y);
+#pragma unroll
+    for (int r = 0; r < 12; ++r) work[12 * c + eig_row_to_coord(r)] = y[r];
+  }
+  // ---- block inverse iteration on R R^T ---------------------------------------------------------
+  T rinv[10];
+  {
+    T rmax = T(0);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rmax = fmax(rmax, R_::abs(A[i][i]));
+    const T floor_ = fmax(rmax * R_::pivot_floor, kTiny);  // a numerically zero pivot: keep the solves finite
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rinv[i] = R_::rcp(R_::copysign(fmax(R_::abs(A[i][i]), floor_), A[i][i]));
+  }
+  T w0[10] = {T(1.0), T(-0.7), T(0.5), T(0.9), T(-0.4), T(0.8), T(-0.6), T(0.3), T(-0.95), T(0.65)};
+  T w1[10] = {T(0.6), T(0.85), T(-0.45), T(0.35), T(0.75), T(-0.9), T(-0.5), T(0.55), T(0.4), T(-0.8)};
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+    // Both substitutions in their column-oriented (axpy) form: once an unknown is final it is eliminated from
+    // all the remaining equations with independent FMAs, so the dependent chain is 10 x (mul, fma) instead of
+    // the 55 serial FMAs of the row-oriented loops.
+    // R a = w (back substitution), in place
+#pragma unroll
+    for (int j = 9; j >= 0; --j) {
+      w0[j] *= rinv[j];
+      w1[j] *= rinv[j];
+#pragma unroll
+      for (int i = 0; i < j; ++i) {
+        w0[i] = fma(-A[i][j], w0[j], w0[i]);
+        w1[i] = fma(-A[i][j], w1[j], w1[i]);
+      }
+    }
+    // R^T y = a (forward substitution), in place
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      w0[j] *= rinv[j];
+      w1[j] *= rinv[j];
+#pragma unroll
+      for (int i = j + 1; i < 10; ++i) {
+        w0[i] = fma(-A[j][i], w0[j], w0[i]);
+        w1[i] = fma(-A[j][i], w1[j], w1[i]);
+      }
+    }
+    // Gram-Schmidt
+    T n0 = T(0), d01 = T(0);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      n0 = fma(w0[i], w0[i], n0);
+      d01 = fma(w0[i], w1[i], d01);
+    }
+    const T i0 = R_::rsqrt(fmax(n0, kTiny));
+    const T proj = d01 * i0 * i0;
+    T n1 = T(0);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      w1[i] = fma(-proj, w0[i], w1[i]);
+      w0[i] *= i0;
+      n1 = fma(w1[i], w1[i], n1);
+    }
+    const T i1 = R_::rsqrt(fmax(n1, kTiny));
+#pragma unroll
+    for (int i = 0; i < 10; ++i) w1[i] *= i1;
+  }
+  // ---- Rayleigh-Ritz inside the pair: S = W^T R R^T W, rotate so that S is diagonal ---------------
+  {
+    T s00 = T(0), s01 = T(0), s11 = T(0);
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      T g0 = T(0), g1 = T(0);
+#pragma unroll
+      for (int k = 0; k <= j; ++k) {
+        g0 = fma(A[k][j], w0[k], g0);
+        g1 = fma(A[k][j], w1[k], g1);
+      }
+      s00 = fma(g0, g0, s00);
+      s01 = fma(g0, g1, s01);
+      s11 = fma(g1, g1, s11);
+    }
+    const T h = s11 - s00, gg = s01 + s01;
+    const T q = R_::sqrt(fma(h, h, fma(gg, gg, kTinier)));
+    const T t = gg * R_::rcp(h + R_::copysign(q, h));
+    const T c = R_::rsqrt(fma(t, t, T(1))), sn = c * t;
+    const bool swap = fma(-t, s01, s00) > fma(t, s01, s11);  // v2 = the smaller Ritz value
+    T y2[12], y3[12];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const T a = c * w0[i] - sn * w1[i], b = sn * w0[i] + c * w1[i];
+      y2[i] = swap ? b : a;
+      y3[i] = swap ? a : b;
+    }
+    y2[10] = y2[11] = y3[10] = y3[11] = T(0);
+    // both back-transforms read tau from work[24..33] before v2 is written over it
+    apply_q(y2);
+    apply_q(y3);
+#pragma unroll
+    for (int r = 0; r < 12; ++r) work[24 + eig_row_to_coord(r)] = y2[r], work[36 + eig_row_to_coord(r)] = y3[r];
   }
 }
 

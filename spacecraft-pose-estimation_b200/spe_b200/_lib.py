@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libspe_b200.so")
 
 _lib = None
+ABI_VERSION = 2
 
 
 class SpeError(RuntimeError):
@@ -26,7 +27,7 @@ def lib() -> ctypes.CDLL:
             )
         L = ctypes.CDLL(LIB_PATH)
         _declare(L)
-        if L.spe_abi_version() != 1:
+        if L.spe_abi_version() != ABI_VERSION:
             raise SpeError("libspe_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -49,6 +50,10 @@ def _declare(L):
     L.spe_decode_combined_kpts_f32.restype = c_int
     L.spe_decode_combined_kpts_f32.argtypes = [POINTER(c_void_p), c_int, c_int, ip, c_int, c_int, c_int, c_int, c_int, fp, fp, c_int, fp, ip,
                                                c_void_p]
+    L.spe_boxes_to_center_scale_f64.restype = c_int
+    L.spe_boxes_to_center_scale_f64.argtypes = [dp, c_int, fp, fp, c_void_p]
+    L.spe_pick_boxes_f32.restype = c_int
+    L.spe_pick_boxes_f32.argtypes = [fp, fp, ip, c_int, c_int, c_double, c_double, dp, fp, ip, fp, fp, c_void_p]
     if hasattr(L, "spe_pnp_model_create"):
         L.spe_pnp_model_create.restype = c_int
         L.spe_pnp_model_create.argtypes = [POINTER(c_double), c_int, POINTER(c_double), POINTER(c_double), c_int, POINTER(c_void_p)]
@@ -69,6 +74,12 @@ def _declare(L):
         L.spe_ransac_score_f32.argtypes = [c_void_p, fp, c_int, c_int, c_float, c_double, c_float, c_void_p, c_size_t, c_int, c_void_p]
         L.spe_ransac_select_refit_f32.restype = c_int
         L.spe_ransac_select_refit_f32.argtypes = [c_void_p, c_int, c_int, c_double, fp, up, ip, ip, dp, c_void_p, c_size_t, c_int, c_void_p]
+        L.spe_pnp_minimal_sets_host.restype = c_int
+        L.spe_pnp_minimal_sets_host.argtypes = [c_int, c_int, POINTER(c_int32), POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]
+        L.spe_ransac_replay_f64.restype = c_int
+        L.spe_ransac_replay_f64.argtypes = [c_void_p, c_int, c_int, c_float, c_double, c_void_p, c_size_t, c_void_p]
+        L.spe_ransac_read_budget.restype = c_int
+        L.spe_ransac_read_budget.argtypes = [c_void_p, c_void_p, c_int, c_int, ip, c_void_p]
         L.spe_ransac_debug_scores.restype = c_int
         L.spe_ransac_debug_scores.argtypes = [c_void_p, c_void_p, c_int, c_int, ip, up, c_void_p]
         L.spe_pipeline_workspace_bytes.restype = c_size_t
@@ -82,12 +93,14 @@ FLAG_REFINE_LM = 1
 FLAG_ADAPTIVE = 2
 FLAG_BACKGROUND_TAIL = 4
 FLAG_JACOBI_SVD = 8
+FLAG_EXACT = 16
+MAX_HYPOTHESES = 16384
 DECODE_BACKGROUND = 1
 
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",
-    "spe_decode_kpts_f32", "spe_decode_kpts_ex_f32", "spe_decode_combined_kpts_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
-    "spe_pnp_model_minimal_sets", "spe_pnp_control_entry", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_score_f32",
+    "spe_decode_kpts_f32", "spe_decode_kpts_ex_f32", "spe_decode_combined_kpts_f32", "spe_boxes_to_center_scale_f64", "spe_pick_boxes_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
+    "spe_pnp_model_minimal_sets", "spe_pnp_minimal_sets_host", "spe_pnp_control_entry", "spe_ransac_replay_f64", "spe_ransac_read_budget", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_score_f32",
     "spe_ransac_select_refit_f32", "spe_ransac_debug_scores",
     "spe_pipeline_workspace_bytes", "spe_heatmap_to_pose_f32",
 )

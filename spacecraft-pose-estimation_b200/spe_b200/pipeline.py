@@ -47,6 +47,10 @@ def all_gather_rows(local, n_total: int, group=None):
         return local
     world = dist.get_world_size(group)
     per = (n_total + world - 1) // world
+    if n_total == per * world:  # even shards: one collective, no padding, no trimming
+        out = torch.empty((n_total,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
     pad = torch.zeros((per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     out = torch.empty((world * per,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
@@ -59,23 +63,35 @@ def all_gather_rows(local, n_total: int, group=None):
 
 
 class HeatmapToPose:
-    """The whole stage for one landmark/camera model on one GPU."""
+    """The whole stage for one landmark/camera model on one GPU.
+
+    hypotheses  minimal sets per frame scored by the FP32 hypothesis kernel (BASELINE.json: 256)
+    iterations  cv2's iterationsCount (10000 in the reference, export_predicted_poses_real.py:201)
+    exact       True (default): the winner comes from the float64 replay of cv2's own sequential loop
+                (SPE_FLAG_EXACT, the parity path; hypotheses may then be 0); False: cv2's acceptance rule over the
+                FP32 counts of the first `hypotheses` draws
+    """
 
     def __init__(self, model: CameraModel, hypotheses: int = 256, reproj_err: float = 15.0, confidence: float = 0.99,
                  conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, post_process: bool = True, device=None, refine: str | None = None,
-                 adaptive: bool = False):
+                 adaptive: bool = False, exact: bool = True, iterations: int = 10000):
         torch = _lib.require_cuda()
         self.model = model
         self.hypotheses = int(hypotheses)
+        self.iterations = max(int(iterations), self.hypotheses)
+        self.exact = bool(exact)
         self.reproj_err = float(reproj_err)
         self.confidence = float(confidence)
         self.conf_floor = float(conf_floor)
         self.post_process = bool(post_process)
         if refine not in (None, "lm"):
             raise ValueError("refine must be None or 'lm'")
+        if self.hypotheses < (0 if self.exact else 1):
+            raise ValueError("hypotheses must be positive unless exact=True")
         # adaptive=True scores only the hypotheses cv2's shrinking budget could reach (identical results)
-        self.flags = (_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0)
-        self.solver = PnPSolver(model.landmarks, model.K, model.dist, max_hypotheses=self.hypotheses, device=device)
+        self.flags = ((_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0) |
+                      (_lib.FLAG_EXACT if self.exact else 0))
+        self.solver = PnPSolver(model.landmarks, model.K, model.dist, max_hypotheses=self.iterations, device=device)
         self.device = self.solver.device
         self._L = _lib.lib()
         self._ws = None
@@ -193,114 +209,91 @@ class HeatmapToPose:
 class StreamedHeatmapToPose:
     """Software-pipelined executor for a STREAM of device-resident batches.
 
-    The stage has a throughput-bound front (decode + hypothesis scoring, ~1.5 ms per 4096 frames)
-    and a latency-bound tail (cv2-sequential selection + float64 refit, ~0.3 ms whatever the batch
-    size, occupying about one warp per SM).  Submitting batch i+1's front on the main stream while
-    batch i's tail (and the final all_gather of its poses) runs on a side stream hides the tail:
-    spe_ransac_score_f32 / spe_ransac_select_refit_f32 are the two halves of the C ABI call.
-    Results of a submit() are valid after wait(slot) or drain().  `depth` batches are in flight, each with its own buffers.
+    The stage has a throughput-bound front (decode + FP32 hypothesis scoring) and a latency-bound tail (float64 replay
+    of cv2's loop, selection, float64 refit: ~0.3 ms whatever the batch size).  Submitting batch i+1's front on the
+    caller's stream while batch i's tail runs on a side stream hides the tail: spe_ransac_score_f32 /
+    spe_ransac_replay_f64 / spe_ransac_select_refit_f32 are the stages of the C ABI call.
+    Results of a submit() are valid after wait(slot) or drain().  `depth` batches are in flight, each with its own
+    workspace.  Outputs go to the slot's own tensors or to caller-provided ones (submit(..., out=StageOutput(...)), e.g.
+    views of one [K*B,7] buffer that is all_gathered once at the end of the job).
     """
 
-    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 2, gather_total: int | None = None, want_rt: bool = False,
-                 tail_after_decode: bool = False, tail_priority: int = 0, overlap_decode: bool = False):
+    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 2, want_rt: bool = False, tail_priority: int = 0):
         torch = stage._torch
-        self.stage, self.B, self.depth, self.gather_total = stage, int(batch), int(depth), gather_total
+        self.stage, self.B, self.depth = stage, int(batch), int(depth)
         dev, J, H = stage.device, stage.solver.J, stage.hypotheses
         self._L = stage._L
-        self.main = torch.cuda.current_stream(dev)
         self.side = torch.cuda.Stream(dev, priority=tail_priority)  # (priority makes no measurable difference)
-        # overlap_decode: the HBM-bound decode of batch i+1 runs on its own (high-priority) stream as small background
-        # CTAs (SPE_DECODE_BACKGROUND) under the compute-bound hypothesis scoring of batch i
-        self.overlap_decode = bool(overlap_decode)
-        self.dstream = torch.cuda.Stream(dev, priority=-1) if self.overlap_decode else None
-        # ... and the scoring on an internal stream too: an event recorded on the caller's stream must cover the
-        # producer of the inputs only, not the previous batch's scoring
-        self.cstream = torch.cuda.Stream(dev) if self.overlap_decode else self.main
         self.ws_bytes = int(self._L.spe_ransac_workspace_bytes(stage.solver.handle, self.B, H))
         self.slots = []
+        cur = torch.cuda.current_stream(dev)
         for _ in range(self.depth):
             done = torch.cuda.Event()
-            done.record(self.main)
+            done.record(cur)
             self.slots.append({
-                "out": StageOutput(torch.empty((self.B, 7), dtype=torch.float32, device=dev), torch.empty((self.B,), dtype=torch.int32, device=dev),
+                "own": StageOutput(torch.empty((self.B, 7), dtype=torch.float32, device=dev), torch.empty((self.B,), dtype=torch.int32, device=dev),
                                    torch.empty((self.B,), dtype=torch.int32, device=dev), torch.empty((self.B, J, 3), dtype=torch.float32, device=dev)),
+                "out": None,
                 "rt": torch.empty((self.B, 12), dtype=torch.float64, device=dev) if want_rt else None,
                 "ws": torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev),
-                "scored": torch.cuda.Event(), "decoded": torch.cuda.Event(), "input": torch.cuda.Event(), "done": done, "gathered": None,
+                "scored": torch.cuda.Event(), "done": done,
             })
         self._next = 0
         self._pending = None
-        self.tail_after_decode = bool(tail_after_decode)
 
-    def submit(self, hm, center, scale, decode_events=None):
-        """Enqueue one batch.  Returns the slot dict: slot['out'] (StageOutput), slot['gathered']
-        (the [N_total,7] tensor if gather_total was given), slot['done'] (event).  The batch's tail is
-        enqueued by the NEXT submit() (behind that batch's decode), or by wait()/drain()."""
+    def submit(self, hm, center, scale, out: StageOutput | None = None, decode_events=None):
+        """Enqueue one batch on torch's CURRENT stream (the stream that produced hm / center / scale).  Returns the slot
+        dict: slot['out'] (StageOutput; `out` if given, with out.kpts optional), slot['done'] (event).  The inputs are only
+        read by kernels of the current stream, so the caller's usual stream-ordered reuse of them stays safe."""
         torch = self.stage._torch
         st = self.stage
         B, J, H, W = hm.shape
         assert B == self.B and J == st.solver.J and hm.is_contiguous() and hm.dtype == torch.float32
+        main = torch.cuda.current_stream(st.device)
         slot = self.slots[self._next]
         self._next = (self._next + 1) % self.depth
         if slot is self._pending:  # depth 1: this slot's previous tail has to run first
             self.flush()
-        out, ws = slot["out"], slot["ws"]
-        main = self.main
-        if self.overlap_decode:
-            ds = self.dstream
-            slot["input"].record(main)  # whatever produced hm/center/scale on the caller's stream
-            ds.wait_event(slot["input"])
-            ds.wait_event(slot["done"])  # the tail that last used this slot's buffers has finished
-            if decode_events is not None:
-                decode_events[0].record(ds)
-            _lib.check(self._L.spe_decode_kpts_ex_f32(hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(st.post_process),
-                                                      out.kpts.data_ptr(), None, _lib.DECODE_BACKGROUND, ds.cuda_stream), "spe_decode_kpts_ex_f32")
-            if decode_events is not None:
-                decode_events[1].record(ds)
-            slot["decoded"].record(ds)
-            self.cstream.wait_event(slot["decoded"])
-        else:
-            main.wait_event(slot["done"])  # the tail that last used this slot's buffers has finished
-            if decode_events is not None:
-                decode_events[0].record(main)
-            _lib.check(self._L.spe_decode_kpts_f32(hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(st.post_process),
-                                                   out.kpts.data_ptr(), None, main.cuda_stream), "spe_decode_kpts_f32")
-            if decode_events is not None:
-                decode_events[1].record(main)
-            slot["decoded"].record(main)
-        # tail_after_decode: the previous batch's tail is enqueued behind THIS batch's decode, so that the decode has
-        # every SM to itself (0.115 ms instead of 0.150 in the step) — but the step is slower that way (0.745 vs
-        # 0.707 ms, tools/pipe_ab.py): the dynamically scheduled decode tolerates the tail's whole-SM CTAs well, and
-        # the tail hides better under decode + hypotheses than under the hypotheses alone.  Off by default.
-        if self._pending is not None:
-            self._enqueue_tail(self._pending, after=slot["decoded"] if self.tail_after_decode else None)
-        cs = self.cstream
+        own = slot["own"]
+        if out is None:
+            out = own
+        elif out.kpts is None:
+            out = StageOutput(out.pose7, out.inlier_mask, out.status, own.kpts)
+        slot["out"] = out
+        ws = slot["ws"]
+        main.wait_event(slot["done"])  # the tail that last used this slot's workspace has finished
+        if decode_events is not None:
+            decode_events[0].record(main)
+        _lib.check(self._L.spe_decode_kpts_f32(hm.data_ptr(), B, J, H, W, center.data_ptr(), scale.data_ptr(), int(st.post_process),
+                                               out.kpts.data_ptr(), None, main.cuda_stream), "spe_decode_kpts_f32")
+        if decode_events is not None:
+            decode_events[1].record(main)
         _lib.check(self._L.spe_ransac_score_f32(st.solver.handle, out.kpts.data_ptr(), B, st.hypotheses, st.reproj_err, st.confidence,
-                                                st.conf_floor, ws.data_ptr(), ws.numel(), st.flags, cs.cuda_stream), "spe_ransac_score_f32")
-        slot["scored"].record(cs)
+                                                st.conf_floor, ws.data_ptr(), ws.numel(), st.flags, main.cuda_stream), "spe_ransac_score_f32")
+        slot["scored"].record(main)
         self._pending = slot
-        if not self.tail_after_decode:
-            self.flush()
+        self.flush()
         return slot
 
-    def _enqueue_tail(self, slot, after=None):
-        torch = self.stage._torch
+    def _enqueue_tail(self, slot):
         st, side, out, ws = self.stage, self.side, slot["out"], slot["ws"]
         side.wait_event(slot["scored"])
-        if after is not None:
-            side.wait_event(after)
+        if st.exact:
+            _lib.check(self._L.spe_ransac_replay_f64(st.solver.handle, self.B, st.hypotheses, st.reproj_err, st.confidence, ws.data_ptr(),
+                                                     ws.numel(), side.cuda_stream), "spe_ransac_replay_f64")
         _lib.check(self._L.spe_ransac_select_refit_f32(st.solver.handle, self.B, st.hypotheses, st.confidence, out.pose7.data_ptr(),
                                                        out.inlier_mask.data_ptr(), out.status.data_ptr(), None,
                                                        slot["rt"].data_ptr() if slot["rt"] is not None else None, ws.data_ptr(), ws.numel(),
                                                        st.flags | _lib.FLAG_BACKGROUND_TAIL, side.cuda_stream), "spe_ransac_select_refit_f32")
-        if self.gather_total is not None:
-            with torch.cuda.stream(side):
-                slot["gathered"] = all_gather_rows(out.pose7, self.gather_total)
         slot["done"].record(side)
+        # outputs (and a caller-provided `out`) were allocated on other streams and are written here: tell the allocator
+        for t in (out.pose7, out.inlier_mask, out.status, out.kpts, ws, slot["rt"]):
+            if t is not None:
+                t.record_stream(side)
         self._pending = None
 
     def flush(self):
-        """Enqueue the tail of the most recent batch now (nothing follows it to hide behind)."""
+        """Enqueue the tail of the most recent batch now."""
         if self._pending is not None:
             self._enqueue_tail(self._pending)
 
@@ -310,7 +303,8 @@ class StreamedHeatmapToPose:
         slot["done"].synchronize()
 
     def drain(self):
-        """Make the main stream wait for every tail in flight."""
+        """Make torch's current stream wait for every tail in flight."""
         self.flush()
+        main = self.stage._torch.cuda.current_stream(self.stage.device)
         for slot in self.slots:
-            self.main.wait_event(slot["done"])
+            main.wait_event(slot["done"])

@@ -9,11 +9,14 @@ passes between its stages (preds float32 [N,J,3] = x, y, maxval; lib/dataset/PEd
 as a NumPy array or a torch CUDA tensor; `solvePnPRansac` keeps cv2's single-frame signature and
 return tuple for call-site compatibility.
 
-On the GPU every one of the first `hypotheses` minimal sets of OpenCV's fixed-seed RNG is scored;
-the winner is then chosen by replaying cv2's sequential rule (first strictly better inlier count,
-adaptively shrinking budget), so the result equals cv2's whenever cv2 would have stopped within
-`hypotheses` draws (always for n <= 11: the budget after the first 5-inlier model is <= 235).
-All arithmetic is in libspe_b200.so (csrc/ransac_epnp.cu); there is no CPU path here.
+Two selections are available (include/spe_b200.h):
+  exact=True (default)  cv2's own sequential, adaptive loop replayed in float64 up to `max_hypotheses`
+                        (= cv2's iterationsCount, 10000 in the reference): the parity path.
+  exact=False           every distinct one of the first `hypotheses` minimal sets of OpenCV's fixed-seed RNG is
+                        scored in FP32 and cv2's acceptance rule is replayed over those counts: equal to cv2
+                        whenever FP32 and float64 agree on the hypotheses cv2 looks at and cv2 stops within
+                        `hypotheses` draws (`PoseBatch.budget` tells when it would not have).
+All arithmetic is in libspe_b200.so (csrc/ransac_*.cu); there is no CPU path here.
 """
 from __future__ import annotations
 
@@ -36,6 +39,7 @@ class PoseBatch:
     status: object  # [B] int32, FRAME_*
     winner: object  # [B] int32 accepted hypothesis index (-1: none)
     rt: object  # [B,12] float64 row-major R then t
+    budget: object = None  # [B] int32: hypotheses cv2's loop looks at (exact) / would still want (fast: > hypotheses = cut short)
 
 
 def _dptr(arr, ctype):
@@ -45,7 +49,9 @@ def _dptr(arr, ctype):
 class PnPSolver:
     """Immutable landmark/camera model on one device + reusable scratch space."""
 
-    def __init__(self, landmarks, K, dist=None, max_hypotheses: int = 256, device=None):
+    def __init__(self, landmarks, K, dist=None, max_hypotheses: int = 10000, device=None):
+        """max_hypotheses = cv2's iterationsCount (10000 in the reference's call): the budget cv2's loop starts with
+        and the upper bound of `hypotheses` in solve()."""
         torch = _lib.require_cuda()
         self._L = _lib.lib()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -104,11 +110,12 @@ class PnPSolver:
     # -- the batched solve
     def solve_device(self, kpts, hypotheses: int = 256, reproj_err: float = 15.0, confidence: float = 0.99,
                      conf_floor: float = ADAPTIVE_CONFIDENCE_FILTER, want_rt: bool = True, refine: str | None = None,
-                     adaptive: bool = False, eig: str = "qr") -> PoseBatch:
+                     adaptive: bool = False, eig: str = "qr", exact: bool = True, want_budget: bool = True) -> PoseBatch:
         """kpts [B,J,3] float32 CUDA contiguous -> PoseBatch of CUDA tensors.  Enqueues on torch's
-        current stream and does not synchronise.  eig="jacobi" scores the hypotheses with the full
-        Jacobi SVD of M^T instead of the default QR + inverse iteration (A/B and tests).  refine="lm" adds a reprojection-error
-        Levenberg-Marquardt step on the inliers (cv2.solvePnPRefineLM's result); the reference does
+        current stream and does not synchronise.  `hypotheses` minimal sets per frame are scored in FP32 (0 with
+        exact=True: none); exact=True selects by the float64 replay of cv2's loop.  eig="jacobi" (development builds
+        of the library only) scores the hypotheses with the full Jacobi SVD of M^T.  refine="lm" adds a
+        reprojection-error Levenberg-Marquardt step on the inliers (cv2.solvePnPRefineLM's result); the reference does
         not do that, so it is off by default."""
         torch = _lib.require_cuda()
         if refine not in (None, "lm"):
@@ -119,25 +126,30 @@ class PnPSolver:
         B, J, three = kpts.shape
         if J != self.J or three != 3:
             raise ValueError(f"kpts must be [B,{self.J},3]")
-        if not (1 <= hypotheses <= self.max_hypotheses):
-            raise ValueError(f"hypotheses must be in [1, {self.max_hypotheses}]")
+        hypotheses = min(int(hypotheses), self.max_hypotheses) if exact else int(hypotheses)
+        if not ((0 if exact else 1) <= hypotheses <= self.max_hypotheses):
+            raise ValueError(f"hypotheses must be in [{0 if exact else 1}, {self.max_hypotheses}]")
         dev = kpts.device
         pose7 = torch.empty((B, 7), dtype=torch.float32, device=dev)
         mask = torch.empty((B,), dtype=torch.int32, device=dev)
         status = torch.empty((B,), dtype=torch.int32, device=dev)
         winner = torch.empty((B,), dtype=torch.int32, device=dev)
         rt = torch.empty((B, 12), dtype=torch.float64, device=dev) if want_rt else None
+        budget = torch.empty((B,), dtype=torch.int32, device=dev) if want_budget else None
         ws = self.workspace(B, hypotheses)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        flags = ((_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0) |
+                 (_lib.FLAG_JACOBI_SVD if eig == "jacobi" else 0) | (_lib.FLAG_EXACT if exact else 0))
         with torch.cuda.device(dev):
             _lib.check(self._L.spe_ransac_epnp_f32(self._handle, kpts.data_ptr(), B, int(hypotheses), float(reproj_err),
                                                    float(confidence), float(conf_floor), pose7.data_ptr(), mask.data_ptr(),
                                                    status.data_ptr(), winner.data_ptr(), rt.data_ptr() if want_rt else None,
-                                                   ws.data_ptr(), ws.numel(),
-                                                   (_lib.FLAG_REFINE_LM if refine == "lm" else 0) | (_lib.FLAG_ADAPTIVE if adaptive else 0) |
-                                                   (_lib.FLAG_JACOBI_SVD if eig == "jacobi" else 0), stream),
+                                                   ws.data_ptr(), ws.numel(), flags, stream),
                        "spe_ransac_epnp_f32")
-        return PoseBatch(pose7, mask, status, winner, rt)
+            if want_budget:
+                _lib.check(self._L.spe_ransac_read_budget(self._handle, ws.data_ptr(), B, int(hypotheses), budget.data_ptr(), stream),
+                           "spe_ransac_read_budget")
+        return PoseBatch(pose7, mask, status, winner, rt, budget)
 
     def solve(self, kpts, **kw) -> PoseBatch:
         """NumPy in -> NumPy out, torch CUDA in -> torch CUDA out."""
@@ -145,7 +157,7 @@ class PnPSolver:
         if isinstance(kpts, np.ndarray):
             t = torch.from_numpy(np.ascontiguousarray(kpts, np.float32)).to(self.device)
             out = self.solve_device(t, **kw)
-            return PoseBatch(*[None if x is None else x.cpu().numpy() for x in (out.pose7, out.inlier_mask, out.status, out.winner, out.rt)])
+            return PoseBatch(*[None if x is None else x.cpu().numpy() for x in (out.pose7, out.inlier_mask, out.status, out.winner, out.rt, out.budget)])
         return self.solve_device(kpts.to(self.device, torch.float32).contiguous(), **kw)
 
     def hypothesis_scores(self, B: int, hypotheses: int):
@@ -190,7 +202,8 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs=None, fla
 
     Returns (ret, rvec (3,1) float64, tvec (3,1) float64, inliers (k,1) int32 or None).
     Raises ValueError for fewer than 4 points (cv2 raises cv2.error) and NotImplementedError for
-    exactly 4 points (cv2 switches to P3P).  `iterationsCount` is capped at 4096 hypotheses.
+    exactly 4 points (cv2 switches to P3P).  `iterationsCount` is capped at 16384.  The result is cv2's loop replayed
+    in float64 (exact=True, no FP32 scoring).
     """
     if flags != SOLVEPNP_EPNP:
         raise NotImplementedError("only flags=cv2.SOLVEPNP_EPNP is implemented (the reference's setting)")
@@ -205,7 +218,7 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs=None, fla
         raise NotImplementedError("n == 4 takes OpenCV's P3P kernel, which is out of scope")
     if n > 32:
         raise ValueError("at most 32 points per frame")
-    H = int(min(max(iterationsCount, 1), 4096))
+    H = int(min(max(iterationsCount, 1), _lib.MAX_HYPOTHESES))
     K = np.ascontiguousarray(cameraMatrix, np.float64)
     d = None if distCoeffs is None else np.asarray(distCoeffs, np.float64).ravel()
     key = (obj.tobytes(), K.tobytes(), None if d is None else d.tobytes(), H)
@@ -215,7 +228,7 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs=None, fla
             _solver_cache.clear()
         solver = _solver_cache[key] = PnPSolver(obj, K, d, max_hypotheses=H)
     kpts = np.concatenate([img, np.ones((n, 1), np.float32)], axis=1)[None]
-    out = solver.solve(kpts, hypotheses=H, reproj_err=float(reprojectionError), confidence=float(confidence), conf_floor=0.5)
+    out = solver.solve(kpts, hypotheses=0, exact=True, reproj_err=float(reprojectionError), confidence=float(confidence), conf_floor=0.5)
     ok = int(out.status[0]) == FRAME_OK
     rt = out.rt[0]
     rvec = matrix_to_rvec(rt[:9].reshape(3, 3)).reshape(3, 1) if ok else np.zeros((3, 1))

@@ -41,7 +41,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 
 def test_abi_basics_without_gpu(lib):
-    assert lib.spe_abi_version() == 1
+    assert lib.spe_abi_version() == 2
     assert lib.spe_status_string(0) == b"ok"
     assert b"invalid" in lib.spe_status_string(-1)
     # argument validation happens before any CUDA call
@@ -55,6 +55,9 @@ def test_abi_basics_without_gpu(lib):
     assert lib.spe_pnp_model_create(lm, 3, K, None, 64, ctypes.byref(handle)) == -1  # J < 4
     assert lib.spe_pnp_model_create(lm, 33, K, None, 64, ctypes.byref(handle)) == -1  # J > 32
     assert lib.spe_pnp_model_create(lm, 11, K, None, 0, ctypes.byref(handle)) == -1
+    assert lib.spe_pnp_model_create(lm, 11, K, None, 16385, ctypes.byref(handle)) == -1  # above SPE_MAX_HYPOTHESES
+    assert lib.spe_pnp_model_create(lm, 11, K, None, 10000, ctypes.byref(handle)) == -4  # K with skew / a bad last row: unsupported
+    assert b"unsupported" in lib.spe_status_string(-4) and b"memory" in lib.spe_status_string(-5)
     assert lib.spe_pnp_model_destroy(None) == 0
     assert lib.spe_ransac_workspace_bytes(None, 4, 64) == 0
 
@@ -90,6 +93,8 @@ def test_pose_entry_points_validate_arguments_without_gpu(lib):
     assert lib.spe_ransac_select_refit_f32(None, 4, 64, 0.99, None, None, None, None, None, None, 0, 0, None) == -1
     assert lib.spe_heatmap_to_pose_f32(None, None, 4, 11, 64, 64, None, None, 1, 64, 15.0, 0.99, -1.0, None, None, None, None, None, 0, 0, None) == -1
     assert lib.spe_pipeline_workspace_bytes(None, 4, 11, 64) == 0
+    assert lib.spe_ransac_replay_f64(None, 4, 64, 15.0, 0.99, None, 0, None) == -1
+    assert lib.spe_ransac_read_budget(None, None, 4, 64, None, None) == -1
     assert lib.spe_pnp_model_num_landmarks(None) == -1
     ptrs = (ctypes.c_void_p * 2)(None, None)
     assert lib.spe_decode_combined_kpts_f32(ptrs, 0, 0, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # K < 1
@@ -145,3 +150,37 @@ def test_control_point_table_entries_on_the_host(lib):
         idv = np.array(bad, np.int32)
         assert lib.spe_pnp_control_entry(dp, J, idv.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
                                          entry.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), None) == -1
+
+
+def test_minimal_sets_and_duplicate_free_lists_on_the_host(lib):
+    """spe_pnp_minimal_sets_host (host only): what spe_pnp_model_create uploads for one point count.  The draws must be
+    OpenCV's (oracle.ocv_rng, pinned by SURVEY App. E.2), `slot` must map every draw to the first draw of the same
+    5-subset (as a set), `uniq` must list those first draws in ascending order — so that the distinct sets among the
+    first H draws are a prefix of the list for every H — and the duplicate fractions must be the ones DESIGN.md quotes."""
+    from oracle import ocv_rng
+
+    def host_tables(n, H):
+        sets, slot, uniq = np.zeros((H, 5), np.int32), np.zeros(H, np.int32), np.zeros(H, np.int32)
+        nu = ctypes.c_int32()
+        p = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        assert lib.spe_pnp_minimal_sets_host(n, H, p(sets), p(slot), p(uniq), ctypes.byref(nu)) == 0
+        return sets, slot, uniq, nu.value
+
+    expected_unique = {(11, 256): 191, (11, 1024): 414, (11, 2048): 452}
+    for n, H in ((6, 64), (10, 256), (11, 256), (11, 1024), (11, 2048), (17, 512), (24, 10000), (32, 4096)):
+        sets, slot, uniq, nu = host_tables(n, H)
+        np.testing.assert_array_equal(sets, ocv_rng.minimal_sets(n, H))
+        seen = {}
+        for h in range(H):
+            key = tuple(sorted(sets[h]))
+            if key not in seen:
+                seen[key] = len(seen)
+                assert uniq[seen[key]] == h
+            assert slot[h] == seen[key]
+        assert nu == len(seen) and np.all(uniq[nu:] == -1) and np.all(np.diff(uniq[:nu]) > 0)
+        for cut in (1, 32, H // 2, H):  # prefix property: distinct sets among the first `cut` draws
+            assert len({tuple(sorted(s)) for s in sets[:cut]}) == int(np.searchsorted(uniq[:nu], cut))
+        if (n, H) in expected_unique:
+            assert nu == expected_unique[(n, H)]
+    assert lib.spe_pnp_minimal_sets_host(5, 64, None, None, None, None) == -1
+    assert lib.spe_pnp_minimal_sets_host(11, 0, None, None, None, None) == -1

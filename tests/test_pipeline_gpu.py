@@ -26,7 +26,7 @@ def _stage_vs_oracle(model, fr, hypotheses, min_agree):
         good = pnp_ref.confidence_filter(ref_kpts[b, :, 2])
         if good.sum() < 6:
             continue
-        ok, p7, mask, rv, tv = pnp_ref.pose_from_keypoints(ref_kpts[b], model.landmarks, model.K, model.dist, iterations=hypotheses)
+        ok, p7, mask, rv, tv = pnp_ref.pose_from_keypoints(ref_kpts[b], model.landmarks, model.K, model.dist, iterations=10000)
         assert ok == (int(out.status[b]) == 0), b
         if not ok:
             continue
@@ -171,25 +171,25 @@ def test_streamed_executor_matches_single_calls():
     pipe.drain()
     torch.cuda.synchronize()
     assert torch.equal(again["out"].pose7, last["out"].pose7)
-    # the deferred-tail schedule (tail enqueued behind the next batch's decode) returns the same results
-    pipe2 = StreamedHeatmapToPose(stage, 256, depth=2, tail_after_decode=True)
-    slots = []
-    for hm, c, s in batches[:2]:
-        slot = pipe2.submit(hm, c, s)
-        pipe2.wait(slot)
-        slots.append((slot["out"].pose7.clone(), slot["out"].inlier_mask.clone()))
-    for (p7, mk), e in zip(slots, expect):
-        assert torch.equal(mk, e[1]) and close(p7, e[0], e[1])
-    for hm, c, s in batches:
-        last2 = pipe2.submit(hm, c, s)
-    pipe2.drain()
+    # caller-provided outputs: views of one [K*B, ...] buffer (what bench.py all_gathers once at the end of the job)
+    from spe_b200.pipeline import StageOutput
+
+    K = len(batches)
+    big = StageOutput(torch.empty((K * 256, 7), device="cuda"), torch.empty((K * 256,), dtype=torch.int32, device="cuda"),
+                      torch.empty((K * 256,), dtype=torch.int32, device="cuda"), None)
+    for k, (hm, c, s) in enumerate(batches):
+        sl = slice(k * 256, (k + 1) * 256)
+        pipe.submit(hm, c, s, out=StageOutput(big.pose7[sl], big.inlier_mask[sl], big.status[sl], None))
+    pipe.drain()
     torch.cuda.synchronize()
-    assert torch.equal(last2["out"].pose7, last["out"].pose7)
-    # decode of batch i+1 as background CTAs on its own stream under the scoring of batch i: same results
-    pipe3 = StreamedHeatmapToPose(stage, 256, depth=3, overlap_decode=True)
-    for hm, c, s in batches:
-        last3 = pipe3.submit(hm, c, s)
-    pipe3.drain()
-    torch.cuda.synchronize()
-    assert torch.equal(last3["out"].kpts, expect[-1][3]) and torch.equal(last3["out"].inlier_mask, expect[-1][1])
-    assert torch.equal(last3["out"].pose7, last["out"].pose7)
+    for k, e in enumerate(expect):
+        sl = slice(k * 256, (k + 1) * 256)
+        assert torch.equal(big.inlier_mask[sl], e[1]) and torch.equal(big.status[sl], e[2]) and close(big.pose7[sl], e[0], e[1])
+    # a caller running under its own stream: submit() follows torch's current stream
+    own = torch.cuda.Stream()
+    own.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(own):
+        slot = pipe.submit(*batches[0])
+        pipe.drain()
+    own.synchronize()
+    assert torch.equal(slot["out"].inlier_mask, expect[0][1])

@@ -1,12 +1,15 @@
 """GPU parity of the RANSAC-EPnP kernels against OpenCV (black box) and the white-box oracle.
 
 Bars (north_star): rotation <= 1e-3 deg, translation <= 1e-4 relative, measured with the
-atan2-based angle metric.  5-point EPnP hypotheses are rounding-chaotic: parity is
-defined on (winner inlier mask, final pose), and the winner-mask agreement rate is asserted and
-reported rather than per-hypothesis equality.
+atan2-based angle metric, asserted over EVERY solved frame against cv2.solvePnPRansac at the
+reference's iterationsCount (tests/parity_util.py): a frame whose inlier set differs from cv2's must be
+one where cv2's own answer is decided by rounding noise.  The large populations are in
+tests/test_parity_gpu.py; this file covers the API surface, edge cases and the FP32 scoring stage.
 """
 import numpy as np
 import pytest
+
+from parity_util import assert_parity, population_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -76,18 +79,16 @@ def test_minimal_sets_match_opencv_rng():
 
 
 def test_well_separated_frames_match_cv2_exactly_in_mask_and_pose():
-    """1 px noise, 0-3 gross outliers >= 40 px: every frame must agree (mask and pose)."""
+    """1 px noise, 0-3 gross outliers >= 40 px: every frame must agree (mask and pose), in both selection modes."""
     spe, pnp = _spe()
     m = spe.models.tango()
     kpts = _clean_frames(m, 256, seed=21)
-    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=256)
-    out = s.solve(kpts, hypotheses=256)
-    same, rots, ts, oks = _compare_with_cv2(m, kpts, out, iterations=10000)
-    assert oks.all() and (out.status == 0).all()
-    assert same.mean() >= 0.99, f"winner-mask agreement {same.mean():.4f}"
-    assert rots[same].max() <= ROT_TOL_DEG, rots[same].max()
-    assert ts[same].max() <= T_TOL_REL, ts[same].max()
-    print(f"well-separated: mask agreement {same.mean():.4f}, max rot {rots[same].max():.2e} deg, max t {ts[same].max():.2e}")
+    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=10000)
+    for exact in (True, False):
+        out = s.solve(kpts, hypotheses=256, exact=exact)
+        assert (out.status == 0).all()
+        rep = population_parity(f"well-separated, exact={exact}", m, kpts, out)
+        assert_parity(rep, 1.0 if exact else 0.99)
 
 
 def test_benchmark_workload_agreement(pnp_golden):
@@ -98,18 +99,17 @@ def test_benchmark_workload_agreement(pnp_golden):
     m = spe.models.tango()
     kpts = g["kpts"]
     H = 256
-    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=H)
+    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=10000)
     out = s.solve(kpts, hypotheses=H)
     counts, masks = s.hypothesis_scores(kpts.shape[0], H)
     counts, masks = counts.cpu().numpy(), masks.cpu().numpy().view(np.uint32)
     valid = g["winner"] >= -1
-    # per-hypothesis agreement is statistical (chaotic minimal sets): report it, bound it loosely
+    # per-hypothesis agreement of the FP32 scores is statistical (chaotic minimal sets): report it, bound it loosely
     # (hyp_masks in the golden file are over the compacted visible points; compare counts)
     agree = (counts[valid] == g["hyp_counts"][valid]).mean()
     assert agree > 0.75, agree
+    assert_parity(population_parity("golden benchmark workload", m, kpts, out), 1.0)
     same, rots, ts, oks = _compare_with_cv2(m, kpts, out, iterations=10000)
-    assert same.mean() >= 0.95, same.mean()
-    assert rots[same].max() <= ROT_TOL_DEG and ts[same].max() <= T_TOL_REL, (rots[same].max(), ts[same].max())
     # golden poses (cv2 4.13.0 at generation time)
     for b in np.flatnonzero(same & oks):
         assert (int(out.inlier_mask[b]) & 0xFFFFFFFF) == int(g["inlier_mask"][b])
@@ -117,20 +117,36 @@ def test_benchmark_workload_agreement(pnp_golden):
     print(f"benchmark workload: per-hypothesis count agreement {agree:.3f}, winner-mask agreement {same.mean():.3f}")
 
 
-def test_larger_benchmark_sample_agreement_rate():
-    from oracle import decode_ref
+def test_duplicate_minimal_sets_are_scored_once_and_read_through_the_slot_table():
+    """n = 11 has only 462 distinct 5-subsets: 60 % of the first 1024 draws repeat an earlier set.  The kernel scores each
+    distinct set once; every repeated draw must report the scores of the first draw of its set, and a frame with fewer
+    visible points (its own, shorter list of distinct sets) must not be disturbed by its neighbours."""
+    from oracle import ocv_rng
 
     spe, pnp = _spe()
     m = spe.models.tango()
-    fr = spe.synth.make_frames(m, 512, 64, 64, seed=spe.synth.BASE_SEED + 11)
-    p, mv = decode_ref.get_final_preds_fast(True, fr.heatmaps, fr.center, fr.scale)
-    kpts = np.concatenate([p, mv], -1).astype(np.float32)
-    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=256)
-    out = s.solve(kpts, hypotheses=256)
-    same, rots, ts, oks = _compare_with_cv2(m, kpts, out, iterations=10000)
-    assert same.mean() >= 0.97, same.mean()
-    assert rots[same].max() <= ROT_TOL_DEG and ts[same].max() <= T_TOL_REL, (rots[same].max(), ts[same].max())
-    print(f"512 synthetic frames: winner-mask agreement {same.mean():.4f}; max rot {rots[same].max():.2e} deg, max t {ts[same].max():.2e}")
+    kpts = _clean_frames(m, 48, seed=77, max_outliers=2)
+    kpts[::3, 5, 2] = 0.0  # every third frame: 10 visible points
+    kpts[1::6, 2, 2] = 0.0
+    H = 1024
+    s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=H)
+    out = s.solve(kpts, hypotheses=H, exact=False)
+    counts, masks = s.hypothesis_scores(kpts.shape[0], H)
+    counts, masks = counts.cpu().numpy(), masks.cpu().numpy().view(np.uint32)
+    for b in range(kpts.shape[0]):
+        n = int((kpts[b, :, 2] > 0).sum())
+        sets = ocv_rng.minimal_sets(n, H)
+        first = {}
+        for h in range(H):
+            key = tuple(sorted(sets[h]))
+            first.setdefault(key, h)
+            assert masks[b, h] == masks[b, first[key]] and counts[b, h] == bin(int(masks[b, h])).count("1"), (b, h)
+        assert len(first) < 0.5 * H
+        # a hypothesis drawn from inliers only must see them all: the scores are real, not left-over memory
+        vis = np.flatnonzero(kpts[b, :, 2] > 0)
+        assert counts[b].max() >= 8 and (masks[b] & ~np.uint32(sum(1 << int(j) for j in vis))).max() == 0
+    assert_parity(population_parity("dedup, FP32 selection", m, kpts, out, iterations=H), 0.97)
+    s.close()
 
 
 def test_frame_status_codes():
@@ -270,9 +286,9 @@ def test_adaptive_budget_gives_identical_results():
     rng = np.random.default_rng(1)
     kpts[:8, :, :2] = rng.uniform(0, 1200, (8, 11, 2))  # junk frames: no model, full budget
     s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=256)
-    full = s.solve(kpts, hypotheses=256)
+    full = s.solve(kpts, hypotheses=256, exact=False)
     full = [x.copy() for x in (full.pose7, full.inlier_mask, full.status, full.winner, full.rt)]
-    ada = s.solve(kpts, hypotheses=256, adaptive=True)
+    ada = s.solve(kpts, hypotheses=256, adaptive=True, exact=False)
     for a, b in zip(full, (ada.pose7, ada.inlier_mask, ada.status, ada.winner, ada.rt)):
         np.testing.assert_array_equal(a, b)
     assert (full[3] >= 32).sum() > 0, "the sample should contain frames whose winner lies in the second pass"
@@ -298,10 +314,15 @@ def test_qr_inverse_iteration_matches_jacobi_svd(case):
     kpts = np.concatenate([p, mv], -1).astype(np.float32)
     H = 256
     s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=H)
-    a = s.solve(kpts, hypotheses=H, eig="qr")
+    a = s.solve(kpts, hypotheses=H, eig="qr", exact=False)
     ca, _ = s.hypothesis_scores(kpts.shape[0], H)
     ca = ca.cpu().numpy()
-    b = s.solve(kpts, hypotheses=H, eig="jacobi")
+    try:
+        b = s.solve(kpts, hypotheses=H, eig="jacobi", exact=False)
+    except spe.SpeError as e:
+        if "unsupported" in str(e):
+            pytest.skip("the Jacobi SVD eigen stage is a development variant (build.py --dev); the shipped library does not contain it")
+        raise
     cb, _ = s.hypothesis_scores(kpts.shape[0], H)
     cb = cb.cpu().numpy()
     solved = (a.status == 0) & (b.status == 0)
@@ -339,28 +360,7 @@ def test_landmark_count_extremes_match_cv2(J):
     H = 128
     s = pnp.PnPSolver(m.landmarks, m.K, m.dist, max_hypotheses=H)
     out = s.solve(kpts, hypotheses=H, conf_floor=0.5)
-    same = []
-    from oracle import pnp_ref
-    import cv2
-
-    for b in range(64):
-        good = kpts[b, :, 2] > 0.5
-        n = int(good.sum())
-        if n < 6:
-            continue
-        ok, rv, tv, inl = pnp_ref.solve_pnp_ransac_cv2(m.landmarks[good], kpts[b, good, :2], m.K, m.dist, iterations=H)
-        gpu_ok = int(out.status[b]) == 0
-        if not ok or not gpu_ok:
-            same.append(ok == gpu_ok)
-            continue
-        ids = np.flatnonzero(good)[np.asarray(inl).ravel()]
-        mask = sum(1 << int(j) for j in ids)
-        eq = (int(out.inlier_mask[b]) & 0xFFFFFFFF) == mask
-        same.append(eq)
-        if eq and len(ids) > 5:
-            r = pnp_ref.rotation_angle_deg(out.rt[b, :9].reshape(3, 3), cv2.Rodrigues(rv)[0])
-            t = float(np.linalg.norm(out.rt[b, 9:] - tv.ravel()) / np.linalg.norm(tv))
-            assert r <= ROT_TOL_DEG and t <= T_TOL_REL, (b, r, t)
-    same = np.array(same)
-    print(f"J={J}: winner-mask agreement with cv2 {same.mean():.3f} on {len(same)} frames")
-    assert same.mean() >= 0.9, same.mean()
+    rep = population_parity(f"J={J}", m, kpts, out, iterations=H, conf_floor=0.5)
+    assert rep.frames >= 48
+    assert_parity(rep, 0.97)
+    s.close()
