@@ -23,6 +23,10 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <new>
+#include <unordered_map>
+
 #include "decode.cuh"
 #include "device_util.cuh"
 
@@ -322,8 +326,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_bulk_kernel(const Decod
 // the chip to itself: the claim for the map after next is issued right behind the bulk copy of the
 // next one, so its L2 round trip hides under the copy.
 //   counter protocol: every warp claims until it draws an index >= n_maps, i.e. exactly
-//   n_maps + (number of warps) claims per launch; atomicInc wraps at that total, so the counter is
-//   back at 0 when the launch ends and needs no reset between stream-ordered launches.
+//   n_maps + (number of warps) claims per launch.  The counter is a per-(device, stream) slot that the
+//   launcher zeroes on the stream before every launch (dyn_counter / launch_dyn below); atomicInc's wrap at
+//   the claim total only keeps the value bounded.
 struct PendingDyn {
   float v;
   int idx;
@@ -713,22 +718,36 @@ cudaError_t launch_bulk(const DecodeArgs& a, int dev, int num_sms, cudaStream_t 
   return cudaGetLastError();
 }
 
-// per-device claim counters for decode_dyn_kernel: a small ring, so that launches in flight on different
-// streams do not share one (stream-ordered launches may: the counter is back at 0 when a launch ends)
-constexpr int kDynCounters = 16;
-inline cudaError_t dyn_counter(int dev, unsigned** out) {
+// Claim counters for decode_dyn_kernel.  The decode entry points take no workspace, so the library keeps one 128-byte
+// slot per (device, stream) it has seen: launches on one stream are ordered and may share a slot, launches on different
+// streams never do.  The slot is zeroed ON THE STREAM before every launch (cudaMemsetAsync), so nothing depends on a
+// previous launch having run to completion.  A process that uses more than kDynSlots streams per device gets nullptr for
+// the others, and those launches take the statically scheduled kernel (same results).
+constexpr int kDynSlots = 1024;
+inline cudaError_t dyn_counter(int dev, cudaStream_t stream, unsigned** out) {
+  static std::mutex mu;
   static unsigned* base[kMaxDevices] = {};
-  static std::atomic<unsigned> next[kMaxDevices];
-  static PerDeviceOnce once;
-  const cudaError_t e = once.run(dev, [dev] {
+  static std::unordered_map<uintptr_t, int>* slots[kMaxDevices] = {};
+  *out = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (base[dev] == nullptr) {
     unsigned* p = nullptr;
-    cudaError_t r = cudaMalloc(&p, sizeof(unsigned) * kDynCounters * 32);  // one counter per 128 B line
-    if (r == cudaSuccess) r = cudaMemset(p, 0, sizeof(unsigned) * kDynCounters * 32);
-    if (r == cudaSuccess) base[dev] = p;
-    return r;
-  });
-  if (e != cudaSuccess) return e;
-  *out = base[dev] + 32 * (next[dev].fetch_add(1, std::memory_order_relaxed) % kDynCounters);
+    const cudaError_t r = cudaMalloc(&p, sizeof(unsigned) * kDynSlots * 32);  // one counter per 128 B line
+    if (r != cudaSuccess) return r;
+    base[dev] = p;
+    slots[dev] = new (std::nothrow) std::unordered_map<uintptr_t, int>();
+  }
+  if (slots[dev] == nullptr) return cudaSuccess;  // no table: static schedule
+  try {
+    auto it = slots[dev]->find(reinterpret_cast<uintptr_t>(stream));
+    if (it == slots[dev]->end()) {
+      if ((int)slots[dev]->size() >= kDynSlots) return cudaSuccess;
+      it = slots[dev]->emplace(reinterpret_cast<uintptr_t>(stream), (int)slots[dev]->size()).first;
+    }
+    *out = base[dev] + 32 * it->second;
+  } catch (...) {  // allocation failure inside the map: static schedule for this launch
+    *out = nullptr;
+  }
   return cudaSuccess;
 }
 
@@ -744,7 +763,10 @@ cudaError_t launch_dyn(const DecodeArgs& a, int dev, int num_sms, cudaStream_t s
   });
   if (e != cudaSuccess) return e;
   unsigned* counter = nullptr;
-  e = dyn_counter(dev, &counter);
+  e = dyn_counter(dev, stream, &counter);
+  if (e != cudaSuccess) return e;
+  if (counter == nullptr) return launch_bulk<kWarps, 1, kChunk, kBatch, kSmemCarveoutPct>(a, dev, num_sms, stream);  // same shape, static split
+  e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
   if (e != cudaSuccess) return e;
   const int ctas_needed = (a.n_maps + kWarps - 1) / kWarps;
   const int grid = ctas_needed < num_sms ? ctas_needed : num_sms;
@@ -754,13 +776,18 @@ cudaError_t launch_dyn(const DecodeArgs& a, int dev, int num_sms, cudaStream_t s
 
 }  // namespace
 
-// dev knob (SPE_DECODE_VARIANT): picks the warps x stages x chunk shape measured in profiles/decode_variants_r1.md
+// development builds (-DSPE_DEV): SPE_DECODE_VARIANT picks one of the warps x stages x chunk shapes measured in
+// profiles/decode_variants_r1.md; the shipped library reads no environment variable and has the default shape only
 static int decode_variant() {
+#ifdef SPE_DEV
   static const int variant = [] {
     const char* v = getenv("SPE_DECODE_VARIANT");
     return v ? atoi(v) : 0;
   }();
   return variant;
+#else
+  return 0;
+#endif
 }
 
 cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
@@ -797,6 +824,7 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
     return launch_dyn<3, 4096, 16>(a, dev, num_sms, stream);
   }
   if (aligned) {
+#ifdef SPE_DEV
     switch (decode_variant()) {
       case 1: return launch_bulk<4, 3, 4096>(a, dev, num_sms, stream);   // 192 KB, 4 warps
       case 2: return launch_bulk<8, 3, 2048>(a, dev, num_sms, stream);   // 192 KB, 8 warps, 8 KB stages
@@ -809,9 +837,14 @@ cudaError_t launch_decode(const DecodeArgs& a, cudaStream_t stream) {
       // carveout (58 %) is the one the pose kernels use too, so an SM never has to drain to switch
       // its shared-memory/L1 split when the kernels of consecutive batches overlap.
       case 7: return launch_bulk<7, 1, 4096, 32, kSmemCarveoutPct>(a, dev, num_sms, stream);  // same shape, static split of the maps
-      // default: that shape with the maps claimed dynamically (decode_dyn_kernel)
-      default: return launch_dyn<7, 4096>(a, dev, num_sms, stream);
+      default: break;
     }
+#endif
+    // 7 warps, one 16 KB stage each = 112 KB of bulk copies in flight per SM (measured best on B200,
+    // profiles/decode_variants_r1.md), maps claimed dynamically (decode_dyn_kernel).  The 132 KB carveout (58 %) is the
+    // one the pose kernels use too, so an SM never has to drain to switch its shared-memory/L1 split when the kernels of
+    // consecutive batches overlap.
+    return launch_dyn<7, 4096>(a, dev, num_sms, stream);
   }
   const int ctas_needed = (a.n_maps + kPlainWarps - 1) / kPlainWarps;
   const int cap = num_sms * 8;

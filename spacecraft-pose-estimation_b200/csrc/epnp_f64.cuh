@@ -3,11 +3,13 @@
 #include <cuda_runtime.h>
 #include <math.h>
 
+#include "epnp_math.cuh"
+
 namespace spe {
 
 // OpenCV's JacobiSVD on the rows of a symmetric n x n matrix (App. B.4): returns the rotated rows
 // normalised (= rows of U^T) sorted by descending singular value.  Sign-defining for the PCA axes.
-__device__ inline void cv_jacobi_rows(double* A, double* w, int n) {
+SPE_HD inline void cv_jacobi_rows(double* A, double* w, int n) {
   const double eps = 2.220446049250313e-16 * 10;
   for (int i = 0; i < n; ++i) {
     double sd = 0;

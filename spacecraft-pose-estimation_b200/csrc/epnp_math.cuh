@@ -7,37 +7,53 @@
 // linearised beta initialisations -> 5 Gauss-Newton steps each -> Procrustes -> best of three.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 
 namespace spe {
 
 // SFU approximations (rcp/sqrt/rsqrt.approx.ftz, ~1 ulp, no slow-path branches).  The FP32 path
 // only scores hypotheses against a 15 px threshold; the one result that is returned to the caller
 // is refit in float64.
-__device__ __forceinline__ float rcp_approx(float x) {
+// (SPE_HD: the float64 instantiations are also compiled for the host by tests/host/exact_eval_host.cu, which checks the
+// replay's arithmetic against cv2 without a GPU; the host versions of the approximations below exist only to compile.)
+#define SPE_HD __host__ __device__
+SPE_HD __forceinline__ float rcp_approx(float x) {
+#ifdef __CUDA_ARCH__
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#else
+  return 1.0f / x;
+#endif
 }
-__device__ __forceinline__ float sqrt_approx(float x) {
+SPE_HD __forceinline__ float sqrt_approx(float x) {
+#ifdef __CUDA_ARCH__
   float r;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#else
+  return sqrtf(x);
+#endif
 }
-__device__ __forceinline__ float rsqrt_approx(float x) {
+SPE_HD __forceinline__ float rsqrt_approx(float x) {
+#ifdef __CUDA_ARCH__
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
+#else
+  return 1.0f / sqrtf(x);
+#endif
 }
 template <typename T>
 struct Real;
 template <>
 struct Real<float> {
-  static __device__ __forceinline__ float sqrt(float x) { return sqrt_approx(x); }
-  static __device__ __forceinline__ float rsqrt(float x) { return rsqrt_approx(x); }
-  static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
-  static __device__ __forceinline__ float rcp(float x) { return rcp_approx(x); }
-  static __device__ __forceinline__ float div(float a, float b) { return a * rcp_approx(b); }
-  static __device__ __forceinline__ float copysign(float m, float s) { return copysignf(m, s); }
+  static SPE_HD __forceinline__ float sqrt(float x) { return sqrt_approx(x); }
+  static SPE_HD __forceinline__ float rsqrt(float x) { return rsqrt_approx(x); }
+  static SPE_HD __forceinline__ float abs(float x) { return fabsf(x); }
+  static SPE_HD __forceinline__ float rcp(float x) { return rcp_approx(x); }
+  static SPE_HD __forceinline__ float div(float a, float b) { return a * rcp_approx(b); }
+  static SPE_HD __forceinline__ float copysign(float m, float s) { return copysignf(m, s); }
   static constexpr float eps = 1.1920929e-7f;
   static constexpr float tiny = 1e-30f;
   static constexpr float pivot_floor = 1e-7f;  // relative size below which a QR pivot counts as zero
@@ -45,12 +61,12 @@ struct Real<float> {
 };
 template <>
 struct Real<double> {
-  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-  static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
-  static __device__ __forceinline__ double abs(double x) { return fabs(x); }
-  static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
-  static __device__ __forceinline__ double div(double a, double b) { return a / b; }
-  static __device__ __forceinline__ double copysign(double m, double s) { return ::copysign(m, s); }
+  static SPE_HD __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static SPE_HD __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  static SPE_HD __forceinline__ double abs(double x) { return fabs(x); }
+  static SPE_HD __forceinline__ double rcp(double x) { return 1.0 / x; }
+  static SPE_HD __forceinline__ double div(double a, double b) { return a / b; }
+  static SPE_HD __forceinline__ double copysign(double m, double s) { return ::copysign(m, s); }
   static constexpr double eps = 2.220446049250313e-16;
   static constexpr double tiny = 1e-280;
   static constexpr double pivot_floor = 1e-15;
@@ -60,7 +76,7 @@ struct Real<double> {
 // Jacobi rotation that orthogonalises two columns with squared norms (a, b) and inner product p:
 // returns (c, s, t = s/c) of  x' = c x - s y,  y' = s x + c y;  new norms a - t p, b + t p.
 template <typename T>
-__device__ __forceinline__ void jacobi_angle(T a, T b, T p, T& c, T& s, T& t) {
+SPE_HD __forceinline__ void jacobi_angle(T a, T b, T p, T& c, T& s, T& t) {
   const T zeta = (b - a) / (T(2) * p);
   t = Real<T>::copysign(T(1), zeta) / (Real<T>::abs(zeta) + Real<T>::sqrt(T(1) + zeta * zeta));
   c = Real<T>::rsqrt(T(1) + t * t);
@@ -69,7 +85,7 @@ __device__ __forceinline__ void jacobi_angle(T a, T b, T p, T& c, T& s, T& t) {
 
 // FP32: 3 MUFU + ~8 FP32 ops.  A rotation only has to be orthogonal to rounding accuracy, which
 // c = rsqrt(1 + t^2), s = c t guarantees irrespective of how exact t is.
-__device__ __forceinline__ void jacobi_angle_fast(float a, float b, float p, float& c, float& s, float& t) {
+SPE_HD __forceinline__ void jacobi_angle_fast(float a, float b, float p, float& c, float& s, float& t) {
   // t = 2p / (h + sign(h) sqrt(h^2 + 4p^2)), h = b - a  ==  sign(zeta) / (|zeta| + sqrt(zeta^2 + 1)) with zeta = h / 2p,
   // in a 3-MUFU dependent chain (sqrt, rcp, rsqrt) instead of 4
   const float h = b - a, gg = p + p;
@@ -79,14 +95,14 @@ __device__ __forceinline__ void jacobi_angle_fast(float a, float b, float p, flo
   s = c * t;
 }
 template <>
-__device__ __forceinline__ void jacobi_angle<float>(float a, float b, float p, float& c, float& s, float& t) {
+SPE_HD __forceinline__ void jacobi_angle<float>(float a, float b, float p, float& c, float& s, float& t) {
   jacobi_angle_fast(a, b, p, c, s, t);
 }
 
 // Householder least squares min |A x - b| for a tiny R x C system held in registers.
 // Zero (masked) columns are skipped and get x = 0.  A and b are overwritten.
 template <typename T, int R, int C>
-__device__ __forceinline__ void lsq_householder(T (&A)[R][C], T (&b)[R], T (&x)[C]) {
+SPE_HD __forceinline__ void lsq_householder(T (&A)[R][C], T (&b)[R], T (&x)[C]) {
   T diag[C];
 #pragma unroll
   for (int k = 0; k < C; ++k) {
@@ -131,7 +147,7 @@ __device__ __forceinline__ void lsq_householder(T (&A)[R][C], T (&b)[R], T (&x)[
 // conditioning is harmless there (agreement with cv2 unchanged, tests/test_pnp_gpu.py) and it costs
 // less than half of the Householder version.
 template <typename T, int R, int C>
-__device__ __forceinline__ void lsq_normal(const T (&A)[R][C], const T (&b)[R], T (&x)[C]) {
+SPE_HD __forceinline__ void lsq_normal(const T (&A)[R][C], const T (&b)[R], T (&x)[C]) {
   T G[C][C], y[C];
 #pragma unroll
   for (int i = 0; i < C; ++i) {
@@ -183,7 +199,7 @@ __device__ __forceinline__ void lsq_normal(const T (&A)[R][C], const T (&b)[R], 
 // kDoubledDiag (FP32 hypothesis path): the squared terms are stored doubled too, L[k][{0,2,5,9}] = 2 |d_i|^2,
 // which turns a Gauss-Newton Jacobian row into four plain dot products (gauss_newton_doubled below).
 template <typename T, bool kDoubledDiag = false>
-__device__ __forceinline__ void build_L(const T (&v)[4][12], T (&L)[6][10]) {
+SPE_HD __forceinline__ void build_L(const T (&v)[4][12], T (&L)[6][10]) {
   constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -209,7 +225,7 @@ __device__ __forceinline__ void build_L(const T (&v)[4][12], T (&L)[6][10]) {
 
 // rho_k = |c_a - c_b|^2 over the six control-point pairs.
 template <typename T>
-__device__ __forceinline__ void build_rho(const T (&cws)[4][3], T (&rho)[6]) {
+SPE_HD __forceinline__ void build_rho(const T (&cws)[4][3], T (&rho)[6]) {
   constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
   for (int k = 0; k < 6; ++k) {
@@ -223,7 +239,7 @@ __device__ __forceinline__ void build_rho(const T (&cws)[4][3], T (&rho)[6]) {
 // kDoubledDiag: L comes from build_L<T, true>; a doubled column halves its unknown (exactly, a power
 // of two), which is undone after the solve.
 template <typename T, bool kNormalEq = false, bool kDoubledDiag = false>
-__device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)[6], int variant, T (&betas)[4]) {
+SPE_HD __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)[6], int variant, T (&betas)[4]) {
   T A[6][5], b[6], x[5];
   const bool v1 = variant == 1, v3 = variant == 3;
 #pragma unroll
@@ -264,7 +280,7 @@ __device__ __forceinline__ void approx_betas(const T (&L)[6][10], const T (&rho)
 // Exactly five Gauss-Newton steps on the six distance constraints (App. B.3i).
 // kNormalEq selects the normal-equation solve (FP32 hypotheses) over Householder QR (float64 refit).
 template <typename T, bool kNormalEq = false>
-__device__ __forceinline__ void gauss_newton(const T (&L)[6][10], const T (&rho)[6], T (&be)[4]) {
+SPE_HD __forceinline__ void gauss_newton(const T (&L)[6][10], const T (&rho)[6], T (&be)[4]) {
 #pragma unroll 1
   for (int it = 0; it < 5; ++it) {
     T A[6][4], r[6], x[4];
@@ -294,7 +310,7 @@ __device__ __forceinline__ void gauss_newton(const T (&L)[6][10], const T (&rho)
 // and the NB Cholesky factorisations / substitutions — short loops dominated by dependent rsqrt and FMA
 // chains — run interleaved, which is the point: NB independent chains per thread for the scheduler.
 template <int NB>
-__device__ __forceinline__ void gauss_newton_doubled_batch(const float (&L)[6][10], const float (&rho)[6], float (&be)[NB][4]) {
+SPE_HD __forceinline__ void gauss_newton_doubled_batch(const float (&L)[6][10], const float (&rho)[6], float (&be)[NB][4]) {
 #pragma unroll 1
   for (int it = 0; it < 5; ++it) {
     float G[NB][4][4], y[NB][4];  // upper triangles only
@@ -372,7 +388,7 @@ __device__ __forceinline__ void gauss_newton_doubled_batch(const float (&L)[6][1
 // planar configurations stay orthonormal; its sign follows the rotated column, which preserves
 // det(U V^T) exactly as a full SVD would give it.
 template <typename T>
-__device__ __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3]) {
+SPE_HD __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3]) {
   T B[3][3], V[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -449,7 +465,7 @@ __device__ __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3])
 // hypothesis).  A single Procrustes is one long dependent chain (dot products -> 3 MUFU -> rotation,
 // 12 times); interleaving NB of them gives the scheduler NB independent chains per thread.
 template <int NB>
-__device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3], float (&R)[NB][3][3]) {
+SPE_HD __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3], float (&R)[NB][3][3]) {
   // One-sided Jacobi on B = A V without accumulating V: the rotated columns are b_j = sigma_j u_j, and the right
   // vectors follow afterwards as v_j = A^T b_j / sigma_j^2 for the two largest columns; the third is their cross
   // product (V is a product of rotations, det +1), exactly as the third u is rebuilt from the other two.
@@ -561,14 +577,14 @@ __device__ __forceinline__ void procrustes_uvt_batch(const float (&A)[NB][3][3],
 // four control points, rows 8..11 the y components.  An x-equation has no y component, so the first
 // five reflectors and the columns they come from live in rows 0..7 only: every inner loop of steps
 // 0..4 (and of their later applications) stops at row 8 instead of 12 (kQrRowEnd).
-__device__ __forceinline__ constexpr int kQrRowEnd(int k) { return k < 5 ? 8 : 12; }
+SPE_HD __forceinline__ constexpr int kQrRowEnd(int k) { return k < 5 ? 8 : 12; }
 // position in the 12-vector (control point j, component c) <- row of A
-__device__ __forceinline__ constexpr int eig_row_to_coord(int r) { return r < 8 ? 3 * (r / 2) + ((r & 1) ? 2 : 0) : 3 * (r - 8) + 1; }
+SPE_HD __forceinline__ constexpr int eig_row_to_coord(int r) { return r < 8 ? 3 * (r / 2) + ((r & 1) ? 2 : 0) : 3 * (r - 8) + 1; }
 
 // T = float: the FP32 hypothesis kernel (SFU approximations, `work` in shared memory); T = double: the float64
 // replay (ransac_exact.cu).
 template <typename T>
-__device__ __forceinline__ void eig_qr_inverse_iteration(T (&A)[12][10], T* __restrict__ work, int iters) {
+SPE_HD __forceinline__ void eig_qr_inverse_iteration(T (&A)[12][10], T* __restrict__ work, int iters) {
   using R_ = Real<T>;
   constexpr T kTiny = T(1e-30), kTinier = T(1e-37);
   // ---- Householder QR, H_k = I - tau_k v_k v_k^T with v_k = (1, A[k+1..][k]) --------------------
@@ -718,9 +734,205 @@ __device__ __forceinline__ void eig_qr_inverse_iteration(T (&A)[12][10], T* __re
   }
 }
 
+// The float64 variant of the stage above for the replay of cv2's loop (ransac_exact.cu): same Householder QR and null
+// space, but the two smallest singular directions of R come from a block of FOUR vectors (two guard vectors) and a 4 x 4
+// Rayleigh-Ritz step.  With a block of two, v3 converges like (sigma_3 / sigma_4)^2 per step, which is ~0.93 when the
+// third and fourth smallest singular values of M nearly coincide (seen on close-range frames: v3 was still a 80-degree
+// mixture after 12 steps and the hypothesis lost all its inliers); with two guard vectors the rate is
+// (sigma_3 / sigma_6)^2.  The FP32 kernel keeps the two-vector block: it only screens.
+template <typename T>
+SPE_HD __forceinline__ void eig_qr_subspace4(T (&A)[12][10], T* __restrict__ work, int iters) {
+  using R_ = Real<T>;
+  constexpr T kTiny = T(1e-30);
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {  // Householder QR, as in eig_qr_inverse_iteration
+    T ss = T(0);
+#pragma unroll
+    for (int i = k + 1; i < kQrRowEnd(k); ++i) ss = fma(A[i][k], A[i][k], ss);
+    const T x0 = A[k][k];
+    const T nn = fma(x0, x0, ss);
+    const bool ok = nn > kTiny;
+    const T nrm = R_::sqrt(nn);
+    const T v0 = x0 + R_::copysign(nrm, x0);
+    const T iv0 = ok ? R_::rcp(v0) : T(0);
+    const T tau = ok ? (R_::abs(x0) + nrm) * R_::rcp(nrm) : T(0);
+    work[24 + k] = tau;
+    A[k][k] = -R_::copysign(nrm, x0);
+#pragma unroll
+    for (int i = k + 1; i < kQrRowEnd(k); ++i) A[i][k] *= iv0;
+#pragma unroll
+    for (int j = k + 1; j < 10; ++j) {
+      T s = A[k][j];
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) s = fma(A[i][k], A[i][j], s);
+      s *= tau;
+      A[k][j] -= s;
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) A[i][j] = fma(-s, A[i][k], A[i][j]);
+    }
+  }
+  auto apply_q = [&](T (&y)[12]) {
+#pragma unroll
+    for (int k = 9; k >= 0; --k) {
+      T s = y[k];
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) s = fma(A[i][k], y[i], s);
+      s *= work[24 + k];
+      y[k] -= s;
+#pragma unroll
+      for (int i = k + 1; i < kQrRowEnd(k); ++i) y[i] = fma(-s, A[i][k], y[i]);
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {  // null space: the last two columns of Q
+    T y[12];
+#pragma unroll
+    for (int r = 0; r < 12; ++r) y[r] = r == 10 + c ? T(1) : T(0);
+    apply_q(y);
+#pragma unroll
+    for (int r = 0; r < 12; ++r) work[12 * c + eig_row_to_coord(r)] = y[r];
+  }
+  T rinv[10];
+  {
+    T rmax = T(0);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rmax = fmax(rmax, R_::abs(A[i][i]));
+    const T floor_ = fmax(rmax * R_::pivot_floor, kTiny);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) rinv[i] = R_::rcp(R_::copysign(fmax(R_::abs(A[i][i]), floor_), A[i][i]));
+  }
+  T w[4][10] = {{T(1.0), T(-0.7), T(0.5), T(0.9), T(-0.4), T(0.8), T(-0.6), T(0.3), T(-0.95), T(0.65)},
+                {T(0.6), T(0.85), T(-0.45), T(0.35), T(0.75), T(-0.9), T(-0.5), T(0.55), T(0.4), T(-0.8)},
+                {T(-0.3), T(0.45), T(0.95), T(-0.65), T(0.2), T(0.5), T(0.85), T(-0.75), T(0.6), T(0.1)},
+                {T(0.8), T(-0.2), T(-0.6), T(-0.5), T(0.9), T(0.15), T(0.7), T(0.95), T(-0.35), T(0.55)}};
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int j = 9; j >= 0; --j) {  // R a = w
+#pragma unroll
+      for (int m = 0; m < 4; ++m) w[m][j] *= rinv[j];
+#pragma unroll
+      for (int i = 0; i < j; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) w[m][i] = fma(-A[i][j], w[m][j], w[m][i]);
+    }
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {  // R^T y = a
+#pragma unroll
+      for (int m = 0; m < 4; ++m) w[m][j] *= rinv[j];
+#pragma unroll
+      for (int i = j + 1; i < 10; ++i)
+#pragma unroll
+        for (int m = 0; m < 4; ++m) w[m][i] = fma(-A[j][i], w[m][j], w[m][i]);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {  // modified Gram-Schmidt
+#pragma unroll
+      for (int p = 0; p < m; ++p) {
+        T d = T(0);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) d = fma(w[p][i], w[m][i], d);
+#pragma unroll
+        for (int i = 0; i < 10; ++i) w[m][i] = fma(-d, w[p][i], w[m][i]);
+      }
+      T n2 = T(0);
+#pragma unroll
+      for (int i = 0; i < 10; ++i) n2 = fma(w[m][i], w[m][i], n2);
+      const T inv = R_::rsqrt(fmax(n2, kTiny));
+#pragma unroll
+      for (int i = 0; i < 10; ++i) w[m][i] *= inv;
+    }
+  }
+  // Rayleigh-Ritz on the block: S = G^T G with G = R^T W (10 x 4); cyclic Jacobi on the 4 x 4 matrix, E = eigenvectors
+  T S[4][4], E[4][4];
+  {
+    T G[4][10];
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+#pragma unroll
+      for (int j = 0; j < 10; ++j) {
+        T g = T(0);
+#pragma unroll
+        for (int k = 0; k <= j; ++k) g = fma(A[k][j], w[m][k], g);
+        G[m][j] = g;
+      }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        T s = T(0);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) s = fma(G[a][j], G[b][j], s);
+        S[a][b] = s;
+        E[a][b] = a == b ? T(1) : T(0);
+      }
+  }
+#pragma unroll 1
+  for (int sweep = 0; sweep < 6; ++sweep) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 4; ++q) {
+        const T apq = S[p][q];
+        const T h = S[q][q] - S[p][p], gg = apq + apq;
+        const T den = h + R_::copysign(R_::sqrt(fma(h, h, gg * gg)), h);
+        const T t = R_::abs(den) > T(0) ? gg / den : T(0);
+        const T c = R_::rsqrt(fma(t, t, T(1))), s = c * t;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // S <- S J
+          const T x = S[k][p], y = S[k][q];
+          S[k][p] = c * x - s * y, S[k][q] = s * x + c * y;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // S <- J^T S,  E <- E J
+          const T x = S[p][k], y = S[q][k];
+          S[p][k] = c * x - s * y, S[q][k] = s * x + c * y;
+          const T ex = E[k][p], ey = E[k][q];
+          E[k][p] = c * ex - s * ey, E[k][q] = s * ex + c * ey;
+        }
+      }
+  }
+  // the two smallest Ritz values
+  int i2 = 0, i3 = 0;
+  {
+    T b2 = S[0][0];
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (S[k][k] < b2) b2 = S[k][k], i2 = k;
+    T b3 = T(0);
+    bool have = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (k != i2 && (!have || S[k][k] < b3)) b3 = S[k][k], i3 = k, have = true;
+  }
+  T y2[12], y3[12];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    T a = T(0), b = T(0);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      // E[m][k] picked without dynamic register indexing
+      T e2 = T(0), e3 = T(0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e2 = k == i2 ? E[m][k] : e2;
+        e3 = k == i3 ? E[m][k] : e3;
+      }
+      a = fma(e2, w[m][i], a);
+      b = fma(e3, w[m][i], b);
+    }
+    y2[i] = a, y3[i] = b;
+  }
+  y2[10] = y2[11] = y3[10] = y3[11] = T(0);
+  apply_q(y2);
+  apply_q(y3);
+#pragma unroll
+  for (int r = 0; r < 12; ++r) work[24 + eig_row_to_coord(r)] = y2[r], work[36 + eig_row_to_coord(r)] = y3[r];
+}
+
 // cv_rotation_matrix_to_quat (pose_estimation/export_predicted_poses_real.py:22-57):
 // scalar-first quaternion, branch on the largest of the four candidate magnitudes.
-__device__ __forceinline__ void rotation_to_quat(const double (&r)[3][3], double (&q)[4]) {
+SPE_HD __forceinline__ void rotation_to_quat(const double (&r)[3][3], double (&q)[4]) {
   const double e0 = sqrt(fmax(1.0 + r[0][0] + r[1][1] + r[2][2], 0.0)) * 0.5;
   const double e1 = sqrt(fmax(1.0 + r[0][0] - r[1][1] - r[2][2], 0.0)) * 0.5;
   const double e2 = sqrt(fmax(1.0 - r[0][0] + r[1][1] - r[2][2], 0.0)) * 0.5;

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "epnp_math.cuh"
 #include "ransac.cuh"
 
 namespace spe {
@@ -11,7 +12,7 @@ namespace spe {
 constexpr unsigned kFullMask = 0xffffffffu;
 
 // RANSACUpdateNumIters: the iteration budget after a model with outlier ratio ep
-__device__ __forceinline__ int update_num_iters(double p, double ep, int max_iters) {
+SPE_HD __forceinline__ int update_num_iters(double p, double ep, int max_iters) {
   p = fmin(fmax(p, 0.0), 1.0);
   ep = fmin(fmax(ep, 0.0), 1.0);
   double num = fmax(1.0 - p, 2.2250738585072014e-308);

@@ -144,3 +144,29 @@ def test_argument_errors():
         spe.get_final_preds(True, np.zeros((2, 3, 8, 8), np.float32), np.zeros((1, 2), np.float32), np.zeros((2, 2), np.float32))
     p, m = spe.get_max_preds(torch.zeros((0, 3, 8, 8), device="cuda"))
     assert p.shape == (0, 3, 2) and m.shape == (0, 3, 1)
+
+
+def test_decode_on_many_concurrent_streams_and_after_an_empty_launch():
+    """The dynamically scheduled kernel draws its maps from a claim counter.  The counter is a per-(device, stream) slot
+    zeroed on the stream before every launch: 40 streams with launches in flight at once (more than the 16-entry ring of
+    round 1), each launching repeatedly, must all decode their own maps completely."""
+    import torch
+
+    import spe_b200
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    streams = [torch.cuda.Stream() for _ in range(40)]
+    inputs = [torch.randn((48 + 3 * i, 5, 64, 64), generator=g, device="cuda") for i in range(len(streams))]
+    torch.cuda.synchronize()
+    results = [[] for _ in streams]
+    for rep in range(3):
+        for i, st in enumerate(streams):
+            with torch.cuda.stream(st):
+                p, m, idx = spe_b200.get_max_preds(inputs[i], return_index=True)
+                results[i].append((p, m, idx))
+    torch.cuda.synchronize()
+    for i, hm in enumerate(inputs):
+        ref = hm.view(hm.shape[0], 5, -1).argmax(2)
+        for p, m, idx in results[i]:
+            assert torch.equal(idx.long(), ref)
+            assert torch.equal(m[..., 0], hm.view(hm.shape[0], 5, -1).amax(2))
