@@ -62,7 +62,13 @@ struct Real<float> {
 template <>
 struct Real<double> {
   static SPE_HD __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-  static SPE_HD __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  static SPE_HD __forceinline__ double rsqrt(double x) {
+#ifdef __CUDA_ARCH__
+    return ::rsqrt(x);
+#else
+    return 1.0 / ::sqrt(x);
+#endif
+  }
   static SPE_HD __forceinline__ double abs(double x) { return fabs(x); }
   static SPE_HD __forceinline__ double rcp(double x) { return 1.0 / x; }
   static SPE_HD __forceinline__ double div(double a, double b) { return a / b; }
@@ -399,6 +405,7 @@ SPE_HD __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3]) {
     }
 #pragma unroll 1
   for (int sweep = 0; sweep < Real<T>::svd3_sweeps; ++sweep) {
+    bool any = false;  // a sweep without a rotation: converged (every later sweep would be the identity too)
 #pragma unroll
     for (int pq = 0; pq < 3; ++pq) {
       const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
@@ -406,6 +413,7 @@ SPE_HD __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3]) {
       const T b = B[0][q] * B[0][q] + B[1][q] * B[1][q] + B[2][q] * B[2][q];
       const T g = B[0][p] * B[0][q] + B[1][p] * B[1][q] + B[2][p] * B[2][q];
       const bool rot = g * g > (Real<T>::eps * Real<T>::eps) * a * b;
+      any = any || rot;
       T c, s, t;
       jacobi_angle<T>(a, b, rot ? g : T(1), c, s, t);
       c = rot ? c : T(1);
@@ -420,6 +428,7 @@ SPE_HD __forceinline__ void procrustes_uvt(const T (&A)[3][3], T (&R)[3][3]) {
         V[r][q] = s * vx + c * vy;
       }
     }
+    if (!any) break;
   }
   T n2[3];
 #pragma unroll

@@ -17,6 +17,10 @@ constexpr int kModelPoints = 5;  // EPnP minimal set used by cv2.solvePnPRansac
 // k_i^2 [3] (squared control-point distances from the centroid: they give rho), pad[2].  The control
 // points themselves are not needed by the hypothesis kernel.
 constexpr int kCtrlEntryFloats = 20;
+// float64 replay (ransac_exact.cu): phases of width 8, 32, 128, 512, 2048, 2048, ...
+constexpr int kReplayMaxWidth = 2048;
+constexpr int kReplayMaxPhases = 16;
+constexpr int kClaimActive = 0, kClaimItem = kReplayMaxPhases, kClaimWords = 2 * kReplayMaxPhases + 2;
 
 struct Camera {
   double fx, fy, cx, cy;
@@ -83,7 +87,11 @@ struct RansacWorkspace {
   int32_t* x_winner;   // [B] accepted hypothesis (-1 none)
   uint32_t* x_mask;    // [B] its inlier mask over the J landmarks
   int32_t* x_visited;  // [B] hypotheses cv2 evaluates before its budget runs out
-  uint32_t* claim;     // [4] work-claim counters, zeroed by the launcher on the call's stream
+  uint32_t* claim;     // [kClaimWords] per-phase work-list lengths and item counters, zeroed by the launcher on the call's stream
+  void* x_state;       // [B] 16-byte per-frame state of cv2's loop between phases (ransac_exact.cu: ReplayState)
+  uint32_t* x_done;    // [B] blocks of the current phase completed per frame
+  int32_t* x_active;   // [2][B] work lists of frames still in cv2's loop (ping-pong between phases)
+  uint32_t* x_masks;   // [B][kReplayMaxWidth] inlier masks of the current phase, one row per work-list entry
   int frames;          // B
   size_t bytes;
 };

@@ -226,7 +226,11 @@ RansacWorkspace carve_workspace(void* base, int J, int B, int H) {
   w.x_winner = static_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
   w.x_mask = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B));
   w.x_visited = static_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
-  w.claim = static_cast<uint32_t*>(take(sizeof(uint32_t) * 4));
+  w.claim = static_cast<uint32_t*>(take(sizeof(uint32_t) * kClaimWords));
+  w.x_state = take(16 * (size_t)B);
+  w.x_done = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B));
+  w.x_active = static_cast<int32_t*>(take(sizeof(int32_t) * 2 * (size_t)B));
+  w.x_masks = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B * kReplayMaxWidth));
   w.frames = B;
   w.bytes = off;
   return w;

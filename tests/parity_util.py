@@ -93,7 +93,7 @@ def population_parity(name, model, kpts, out, iterations=10000, reproj=15.0, whi
         why = []
         if not wb_same:
             why.append("float64 white box disagrees with cv2 too")
-        if pnp_ref.cv2_is_unstable(obj, img, model.K, model.dist, iterations=iterations, reproj=reproj, seed=b):
+        if pnp_ref.cv2_is_unstable(obj, img, model.K, model.dist, trials=64, iterations=iterations, reproj=reproj, seed=b):
             why.append("cv2 changes its own answer under a 1-ulp input perturbation")
         rep.disagree.append((b, "; ".join(why) or "UNEXPLAINED", rot if ok and gpu_ok else float("inf"), tr if ok and gpu_ok else float("inf")))
         if not why:
@@ -102,6 +102,9 @@ def population_parity(name, model, kpts, out, iterations=10000, reproj=15.0, whi
 
 
 def assert_parity(rep: ParityReport, min_agreement: float, max_unexplained: int = 0):
+    """max_unexplained: the chaos probes are statistical (64 one-ulp perturbations of cv2's input catch a frame whose
+    hypotheses flip one time in ten with probability 0.999, one that flips one time in fifty only with 0.73), so large
+    populations get a slack of one frame per thousand; small, well-separated ones none."""
     print(rep.line())
     for d in rep.disagree[:12]:
         print(f"    frame {d[0]}: {d[1]}; pose differs by {d[2]:.3g} deg, {d[3]:.3g} rel-t")

@@ -29,7 +29,7 @@ def test_whole_population_pose_parity_with_cv2_at_10000_iterations(name):
     assert out.budget.max() <= 10000
     rep = population_parity(name, model, kpts, out, iterations=10000, whitebox_sample=96)
     assert rep.frames >= 0.97 * FRAMES
-    assert_parity(rep, MIN_AGREEMENT[name])
+    assert_parity(rep, MIN_AGREEMENT[name], max_unexplained=FRAMES // 1000)
     # the GPU replay is itself a float64 implementation of cv2's algorithm: it must agree with cv2 at least as often as
     # the independent NumPy white box does on the same frames (minus sampling noise of 2 frames)
     assert rep.gpu_same_on_sample >= rep.whitebox_same - 2, rep.line()
@@ -69,9 +69,8 @@ def test_budget_beyond_the_scored_hypotheses_is_followed_to_cv2s_end():
     assert_parity(rep, 0.9)
     assert out.budget.max() > 256, "the sample should contain frames whose cv2 budget exceeds the FP32-scored hypotheses"
     fast = solver.solve(kpts, hypotheses=256, exact=False)
-    assert np.all((fast.budget > 256) == (fast.budget > 256))  # budget is reported ...
     long_frames = out.budget > 256
-    assert np.all(fast.budget[long_frames & (fast.winner == out.winner)] > 256)  # ... and says "cut short" where cv2 went on
+    assert np.all(fast.budget[long_frames & (fast.winner == out.winner)] > 256)  # the FP32-only mode reports "cut short" where cv2 went on
     print(f"cv2 budgets: min {out.budget.min()}, median {int(np.median(out.budget))}, max {out.budget.max()}; "
           f"frames beyond 256 draws: {int(long_frames.sum())}/{B}")
     solver.close()
