@@ -43,6 +43,7 @@ UNIT = "frames/s"
 REPROJ = 15.0
 ITERATIONS = 10000  # the reference's iterationsCount, export_predicted_poses_real.py:201
 CHUNK = 4096
+PIPE_DEPTH = 3  # chunks in flight: the float64 tail of a chunk (~0.6 ms of dependent phases) spans more than one front
 CONFIGS = {
     "A": dict(frames=64, scaling="weak", model="tango", J=11, hm=(64, 64), H=256,
               workload="Tango 11 landmarks, 64 frames of 64x64 heatmaps, 256 RANSAC-EPnP hypotheses (BASELINE.json configs[0])"),
@@ -336,7 +337,7 @@ class Job:
         self.stage = HeatmapToPose(self.model, hypotheses=H, reproj_err=REPROJ, device=dev, exact=exact, iterations=ITERATIONS)
         self.chunk = min(CHUNK, frames_rank)
         self.hm, self.c, self.s = synth.device_heatmaps(self.model, frames_rank, cfg["hm"][0], cfg["hm"][1], seed=synth.BASE_SEED + 101 + rank, device=dev)
-        self.pipe = StreamedHeatmapToPose(self.stage, self.chunk, depth=2) if frames_rank % self.chunk == 0 else None
+        self.pipe = StreamedHeatmapToPose(self.stage, self.chunk, depth=PIPE_DEPTH) if frames_rank % self.chunk == 0 else None
         self.tailpipe = None
         self.flush_buf = None
         if frames_rank * decode_bytes_per_frame(cfg) <= 2 * 126e6:  # small inputs would be served from the L2: flush it between steps
@@ -495,7 +496,7 @@ def gpu_arm(args, rank, local_rank, world):
         from spe_b200.pipeline import HeatmapToPose, StreamedHeatmapToPose
 
         j2.stage = HeatmapToPose(job.model, hypotheses=kw.get("hypotheses", H), reproj_err=REPROJ, device=dev, exact=kw["exact"], iterations=ITERATIONS)
-        j2.pipe = StreamedHeatmapToPose(j2.stage, job.chunk, depth=2)
+        j2.pipe = StreamedHeatmapToPose(j2.stage, job.chunk, depth=PIPE_DEPTH)
         o2 = j2.outputs(steps)
         j2.run_steps(2, o2)
         m2, _, o2, _ = timed_regions(j2, steps, 3, world, dev, gather=True)
@@ -591,7 +592,7 @@ def gpu_arm(args, rank, local_rank, world):
                     "api": "HeatmapToPose.run_host (pinned host tensors, 512-frame chunks, 2 streams), then the all_gather of the poses",
                     "host_affinity": affinity},
             "gpu_launches": job.launches_per_step() * steps,
-            "step_issue": "software-pipelined over 2 streams (StreamedHeatmapToPose): float64 replay + select/refit of chunk i overlap decode + FP32 scoring of chunk i+1",
+            "step_issue": f"software-pipelined, {PIPE_DEPTH} chunks in flight (StreamedHeatmapToPose): the float64 replay + select/refit of a chunk run on the chunk's own side stream under the decode + FP32 scoring of the following chunks",
             "single_chunk_ms": {"frames": B, "decode": decode_alone_ms, "score_fp32": score_ms, "replay_f64": replay_ms, "select_refit_f64": refit_ms,
                                 "total": decode_alone_ms + score_ms + replay_ms + refit_ms, "cv2_hypotheses_looked_at_per_frame": visited_mean},
             "roofline": {"bound": "hbm", "kernel": "decode_dyn_kernel", "achieved": decode_gbs, "peak": hbm_sustained, "unit": "GB/s",
@@ -639,7 +640,7 @@ def sweep_arm(args, cfg, rank, world, dev, sampler):  # noqa: C901
         stage = HeatmapToPose(model, hypotheses=H, reproj_err=REPROJ, device=dev, exact=True, iterations=ITERATIONS)
         for batch in SWEEP_BATCHES:
             ch = min(batch, CHUNK)
-            pipe = StreamedHeatmapToPose(stage, ch, depth=2)
+            pipe = StreamedHeatmapToPose(stage, ch, depth=PIPE_DEPTH)
             n_chunks = max(1, batch // ch)
             out = StageOutput(torch.empty((ch, 7), device=dev), torch.empty((ch,), dtype=torch.int32, device=dev), torch.empty((ch,), dtype=torch.int32, device=dev), None)
 

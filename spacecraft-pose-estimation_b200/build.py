@@ -38,9 +38,13 @@ def _stamp(paths, flags):
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
-    out = OUT_DEV if dev else OUT
-    extra = os.environ.get("SPE_NVCC_EXTRA", "").split() + (["-DSPE_DEV"] if dev else [])
+def build(force: bool = False, verbose: bool = False, dev: bool = False, out: str | None = None, extra_flags=()) -> str:
+    """out / extra_flags: A/B builds (tools/ab_builds.py), e.g. another register budget into another file."""
+    tag = "_dev" if dev else ""
+    if out is not None:
+        tag = "_" + os.path.splitext(os.path.basename(out))[0]
+    out = out or (OUT_DEV if dev else OUT)
+    extra = os.environ.get("SPE_NVCC_EXTRA", "").split() + (["-DSPE_DEV"] if dev else []) + list(extra_flags)
     flags = NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else [])
     os.makedirs(OBJ, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
@@ -48,7 +52,7 @@ def build(force: bool = False, verbose: bool = False, dev: bool = False) -> str:
     jobs, objs = [], []
     for s in srcs:
         src = os.path.join(CSRC, s)
-        obj = os.path.join(OBJ, s.replace(".cu", "_dev.o" if dev else ".o"))
+        obj = os.path.join(OBJ, s.replace(".cu", tag + ".o"))
         stamp_file = obj + ".stamp"
         stamp = _stamp([src] + hdrs, flags)
         objs.append(obj)

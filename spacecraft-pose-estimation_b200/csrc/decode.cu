@@ -326,9 +326,9 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_bulk_kernel(const Decod
 // the chip to itself: the claim for the map after next is issued right behind the bulk copy of the
 // next one, so its L2 round trip hides under the copy.
 //   counter protocol: every warp claims until it draws an index >= n_maps, i.e. exactly
-//   n_maps + (number of warps) claims per launch.  The counter is a per-(device, stream) slot that the
-//   launcher zeroes on the stream before every launch (dyn_counter / launch_dyn below); atomicInc's wrap at
-//   the claim total only keeps the value bounded.
+//   n_maps + (number of warps) claims per launch.  The counter comes from a per-(device, stream) slot of two
+//   counters used alternately; each launch first zeroes the one the next launch will use (dyn_counter / launch_dyn
+//   below); atomicInc's wrap at the claim total only keeps the value bounded.
 struct PendingDyn {
   float v;
   int idx;
@@ -346,7 +346,7 @@ struct DynLayout {
 };
 
 template <int kWarps, int kChunk, int kBatch>
-__global__ void __launch_bounds__(kWarps * 32, 1) decode_dyn_kernel(const DecodeArgs a, unsigned* __restrict__ counter) {
+__global__ void __launch_bounds__(kWarps * 32, 1) decode_dyn_kernel(const DecodeArgs a, unsigned* __restrict__ counter, unsigned* __restrict__ next_counter) {
   static_assert(kBatch <= 32, "one pending map per lane");
   using Layout = DynLayout<kWarps, kChunk, kBatch>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) decode_dyn_kernel(const Decode
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_counter = 0u;  // the counter of the NEXT launch on this stream (launch_dyn)
   __syncwarp();
   const uint64_t policy = evict_first_policy();
   auto claim = [&]() -> int {  // lane 0 only; >= n_maps: nothing left (and this warp must not claim again)
@@ -720,33 +721,46 @@ cudaError_t launch_bulk(const DecodeArgs& a, int dev, int num_sms, cudaStream_t 
 
 // Claim counters for decode_dyn_kernel.  The decode entry points take no workspace, so the library keeps one 128-byte
 // slot per (device, stream) it has seen: launches on one stream are ordered and may share a slot, launches on different
-// streams never do.  The slot is zeroed ON THE STREAM before every launch (cudaMemsetAsync), so nothing depends on a
-// previous launch having run to completion.  A process that uses more than kDynSlots streams per device gets nullptr for
-// the others, and those launches take the statically scheduled kernel (same results).
+// streams never do.  A slot holds TWO counters used alternately: every launch zeroes, as its first action, the counter
+// the next launch on that stream will draw from, so no launch depends on an earlier one having run to completion (and
+// no memset node sits between two kernels of the stream: that costs an engine switch of ~40 us).  A process that uses
+// more than kDynSlots streams per device gets nullptr for the others, and those launches take the statically scheduled
+// kernel (same results).
 constexpr int kDynSlots = 1024;
-inline cudaError_t dyn_counter(int dev, cudaStream_t stream, unsigned** out) {
+struct DynSlot {
+  int index;
+  unsigned parity;
+};
+inline cudaError_t dyn_counter(int dev, cudaStream_t stream, unsigned** cur, unsigned** next) {
   static std::mutex mu;
   static unsigned* base[kMaxDevices] = {};
-  static std::unordered_map<uintptr_t, int>* slots[kMaxDevices] = {};
-  *out = nullptr;
+  static std::unordered_map<uintptr_t, DynSlot>* slots[kMaxDevices] = {};
+  *cur = *next = nullptr;
   std::lock_guard<std::mutex> lock(mu);
   if (base[dev] == nullptr) {
     unsigned* p = nullptr;
-    const cudaError_t r = cudaMalloc(&p, sizeof(unsigned) * kDynSlots * 32);  // one counter per 128 B line
-    if (r != cudaSuccess) return r;
+    cudaError_t r = cudaMalloc(&p, sizeof(unsigned) * kDynSlots * 32);  // one slot per 128 B line
+    if (r == cudaSuccess) r = cudaMemset(p, 0, sizeof(unsigned) * kDynSlots * 32);
+    if (r != cudaSuccess) {
+      if (p) cudaFree(p);
+      return r;
+    }
     base[dev] = p;
-    slots[dev] = new (std::nothrow) std::unordered_map<uintptr_t, int>();
+    slots[dev] = new (std::nothrow) std::unordered_map<uintptr_t, DynSlot>();
   }
   if (slots[dev] == nullptr) return cudaSuccess;  // no table: static schedule
   try {
     auto it = slots[dev]->find(reinterpret_cast<uintptr_t>(stream));
     if (it == slots[dev]->end()) {
       if ((int)slots[dev]->size() >= kDynSlots) return cudaSuccess;
-      it = slots[dev]->emplace(reinterpret_cast<uintptr_t>(stream), (int)slots[dev]->size()).first;
+      it = slots[dev]->emplace(reinterpret_cast<uintptr_t>(stream), DynSlot{(int)slots[dev]->size(), 0u}).first;
     }
-    *out = base[dev] + 32 * it->second;
+    unsigned* slot = base[dev] + 32 * it->second.index;
+    *cur = slot + 16 * (it->second.parity & 1u);
+    *next = slot + 16 * ((it->second.parity + 1u) & 1u);
+    it->second.parity ^= 1u;
   } catch (...) {  // allocation failure inside the map: static schedule for this launch
-    *out = nullptr;
+    *cur = *next = nullptr;
   }
   return cudaSuccess;
 }
@@ -762,15 +776,13 @@ cudaError_t launch_dyn(const DecodeArgs& a, int dev, int num_sms, cudaStream_t s
     return r;
   });
   if (e != cudaSuccess) return e;
-  unsigned* counter = nullptr;
-  e = dyn_counter(dev, stream, &counter);
+  unsigned *counter = nullptr, *next_counter = nullptr;
+  e = dyn_counter(dev, stream, &counter, &next_counter);
   if (e != cudaSuccess) return e;
   if (counter == nullptr) return launch_bulk<kWarps, 1, kChunk, kBatch, kSmemCarveoutPct>(a, dev, num_sms, stream);  // same shape, static split
-  e = cudaMemsetAsync(counter, 0, sizeof(unsigned), stream);
-  if (e != cudaSuccess) return e;
   const int ctas_needed = (a.n_maps + kWarps - 1) / kWarps;
   const int grid = ctas_needed < num_sms ? ctas_needed : num_sms;
-  decode_dyn_kernel<kWarps, kChunk, kBatch><<<grid, kWarps * 32, smem, stream>>>(a, counter);
+  decode_dyn_kernel<kWarps, kChunk, kBatch><<<grid, kWarps * 32, smem, stream>>>(a, counter, next_counter);
   return cudaGetLastError();
 }
 

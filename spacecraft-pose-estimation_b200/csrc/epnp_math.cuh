@@ -878,11 +878,14 @@ SPE_HD __forceinline__ void eig_qr_subspace4(T (&A)[12][10], T* __restrict__ wor
   }
 #pragma unroll 1
   for (int sweep = 0; sweep < 6; ++sweep) {
+    bool any = false;  // the block has (nearly) converged to eigenvectors: S is close to diagonal, one or two sweeps do
 #pragma unroll
     for (int p = 0; p < 3; ++p)
 #pragma unroll
       for (int q = p + 1; q < 4; ++q) {
         const T apq = S[p][q];
+        if (!(apq * apq > (R_::eps * R_::eps) * R_::abs(S[p][p] * S[q][q]))) continue;
+        any = true;
         const T h = S[q][q] - S[p][p], gg = apq + apq;
         const T den = h + R_::copysign(R_::sqrt(fma(h, h, gg * gg)), h);
         const T t = R_::abs(den) > T(0) ? gg / den : T(0);
@@ -900,6 +903,7 @@ SPE_HD __forceinline__ void eig_qr_subspace4(T (&A)[12][10], T* __restrict__ wor
           E[k][p] = c * ex - s * ey, E[k][q] = s * ex + c * ey;
         }
       }
+    if (!any) break;
   }
   // the two smallest Ritz values
   int i2 = 0, i3 = 0;

@@ -20,7 +20,10 @@ constexpr int kCtrlEntryFloats = 20;
 // float64 replay (ransac_exact.cu): phases of width 8, 32, 128, 512, 2048, 2048, ...
 constexpr int kReplayMaxWidth = 2048;
 constexpr int kReplayMaxPhases = 16;
-constexpr int kClaimActive = 0, kClaimItem = kReplayMaxPhases, kClaimWords = 2 * kReplayMaxPhases + 2;
+constexpr int kReplayPlanMax = 32;      // widest phase 0 (hypothesis index fits 5 bits of an item)
+constexpr int kReplayStateBytes = 32;
+constexpr int kReplayFrameBytes = kMaxLandmarks * (3 * 8 + 2 * 8 + 2 * 4 + 1);  // sizeof(FramePoints)
+constexpr int kClaimActive = 0, kClaimPlanItems = kReplayMaxPhases + 1, kClaimWords = kReplayMaxPhases + 3;
 
 struct Camera {
   double fx, fy, cx, cy;
@@ -88,7 +91,10 @@ struct RansacWorkspace {
   uint32_t* x_mask;    // [B] its inlier mask over the J landmarks
   int32_t* x_visited;  // [B] hypotheses cv2 evaluates before its budget runs out
   uint32_t* claim;     // [kClaimWords] per-phase work-list lengths and item counters, zeroed by the launcher on the call's stream
-  void* x_state;       // [B] 16-byte per-frame state of cv2's loop between phases (ransac_exact.cu: ReplayState)
+  void* x_state;       // [B] kReplayStateBytes per-frame state of cv2's loop between phases (ransac_exact.cu: ReplayState)
+  void* x_frames;      // [B] compacted visible landmarks of every frame (ransac_exact_eval.cuh: FramePoints)
+  int32_t* x_width;    // [B] hypotheses of phase 0 (the predicted length of cv2's loop)
+  uint32_t* x_items;   // [B * kReplayPlanMax] phase-0 work list: frame << 5 | hypothesis
   uint32_t* x_done;    // [B] blocks of the current phase completed per frame
   int32_t* x_active;   // [2][B] work lists of frames still in cv2's loop (ping-pong between phases)
   uint32_t* x_masks;   // [B][kReplayMaxWidth] inlier masks of the current phase, one row per work-list entry

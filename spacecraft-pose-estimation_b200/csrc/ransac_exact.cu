@@ -10,19 +10,23 @@
 //     beta initialisations, five Gauss-Newton steps each with Householder QR, Procrustes, best of three by mean
 //     reprojection error — OpenCV's sequence, oracle/epnp_ref.py), then cv2.projectPoints of all n visible points in
 //     float64, rounded to float32, squared error in float32 <= thr^2 (ransac_exact_eval.cuh);
-//   * the loop is sequential per frame but its length is only known at run time (8 hypotheses finish 75 % of the
-//     benchmark frames, a 5-inlier model of 11 points needs 235, a frame without a model all 10000), so it runs in
-//     PHASES of growing width — hypotheses [0,8), [8,40), [40,168), [168,680), then 2048 at a time — one kernel launch
-//     each, no host synchronisation.  Inside a phase every (frame, hypothesis) still wanted by the frame's budget AT THE
-//     START of the phase is evaluated in parallel (the budget only shrinks, so nothing cv2 looks at is missed and at
-//     most 4x too much is evaluated); the warp that finishes a frame's last block then walks the phase's results in
-//     order with cv2's acceptance rule and RANSACUpdateNumIters, and either finishes the frame or appends it to the next
-//     phase's work list.  A phase whose list is empty is a kernel that exits at once.
-//   * work is drawn from counters in the caller's workspace (zeroed by the launcher on the call's stream): a persistent
-//     grid of warps claims (frame, block) items until the phase is done.
-//
-// The FP32 scores of ransac_score.cu are not read here: which hypotheses decide is cv2's rule, and those are
-// re-evaluated in float64 whatever FP32 said about them.
+//   * the loop is sequential per frame but its length is only known at run time (one hypothesis finishes 30 % of the
+//     benchmark frames, five finish 69 %, a 5-inlier model of 11 points needs 235, a frame without a model all 10000),
+//     so it runs in PHASES, one kernel launch each, no host synchronisation:
+//       phase 0   hypotheses [0, w_b) of frame b, where w_b <= 32 is the length cv2's loop WOULD have if the FP32
+//                 scores were cv2's own (replay_plan_kernel walks them with cv2's rule; 8 when nothing was scored).
+//                 The (frame, hypothesis) pairs of all frames form one dense list, one thread each — no idle lanes;
+//       phase p   hypotheses [0, 32) (whatever phase 0 left of them), [32, 160), [160, 672), then 2048 at a time, of the
+//                 frames still in the loop.
+//     Inside a phase every (frame, hypothesis) still wanted by the frame's budget AT THE START of the phase is
+//     evaluated in parallel (the budget only shrinks, so nothing cv2 looks at is missed); the phase's results are then
+//     walked in order with cv2's acceptance rule and RANSACUpdateNumIters, and the frame either finishes or joins the
+//     next phase's work list.  The FP32 prediction is only a schedule: every hypothesis cv2 looks at is decided in
+//     float64, and a frame whose prediction was too short simply continues in the next phase.  A phase whose list is
+//     empty is a kernel that exits at once.
+//   * work lists and counters live in the caller's workspace and are reset by the first kernel of the call.
+// The FP32 scores of ransac_score.cu never decide anything here: which hypotheses count is cv2's rule, and those are
+// evaluated in float64 whatever FP32 said about them.
 // Why a replay and not per-hypothesis bit-parity: a 5-point EPnP has an exact 2-D null space, so ~8 % of cv2's own
 // hypothesis results are decided by rounding noise (measured: a float64 NumPy restatement reproduces cv2's
 // per-hypothesis inlier count on 92 % of minimal sets whether it uses a port of OpenCV's Jacobi SVD or LAPACK's
@@ -47,161 +51,220 @@ namespace spe {
 
 namespace {
 
-constexpr int kReplayWarps = 4;  // 128 threads x 255 registers: two CTAs per SM
-constexpr int kFirstWidth = 8;   // hypotheses of phase 0: four frames per warp
+#ifndef SPE_REPLAY_CTAS_PER_SM
+#define SPE_REPLAY_CTAS_PER_SM 2  // 128 threads x 255 registers: two CTAs per SM (A/B: tools/ab_builds.py)
+#endif
+constexpr int kReplayWarps = 4;
+constexpr int kReplayCtasPerSm = SPE_REPLAY_CTAS_PER_SM;
+constexpr int kPlanWidthNoScores = 8;
 
 struct ReplayState {  // per frame, between phases
   int32_t niters, max_good, winner;
   uint32_t best_mask;
+  int32_t next;  // first hypothesis cv2's loop has not walked yet
+  int32_t pad[3];
 };
-static_assert(sizeof(ReplayState) == 16, "ReplayState is carved as 16 bytes per frame");
+static_assert(sizeof(ReplayState) == kReplayStateBytes, "ReplayState is carved as kReplayStateBytes per frame");
 
-__device__ __forceinline__ void load_frame(const DevModel& m, const RansacWorkspace& ws, int b, int n, FramePoints& f, int sub, int lanes) {
-  const unsigned vis = ws.vis[b];
-  for (int k = sub; k < n; k += lanes) {
-    const int j = __fns(vis, 0, k + 1);
-#pragma unroll
-    for (int c = 0; c < 3; ++c) f.pw[k][c] = (double)m.landmarks[3 * j + c];
-    const double2 q = ws.und[(size_t)b * m.J + j];
-    // hypotheses see the float32-rounded undistorted point (cv2 keeps the input dtype), App. B.3a
-    f.us[k][0] = (double)(float)q.x * m.cam.fx + m.cam.cx;
-    f.us[k][1] = (double)(float)q.y * m.cam.fy + m.cam.cy;
-    const float2 px = ws.img[(size_t)b * m.J + j];
-    f.img[k][0] = px.x, f.img[k][1] = px.y;
-    f.id[k] = (uint8_t)j;
+__device__ __forceinline__ ReplayState* state_of(const RansacWorkspace& ws, int b) { return reinterpret_cast<ReplayState*>(ws.x_state) + b; }
+__device__ __forceinline__ const FramePoints& frame_of(const RansacWorkspace& ws, int b) { return reinterpret_cast<const FramePoints*>(ws.x_frames)[b]; }
+
+// One acceptance of cv2's loop.
+__device__ __forceinline__ void accept(ReplayState& st, int h, unsigned mask, int n, double confidence) {
+  const int g = __popc(mask);
+  if (g > max(st.max_good, kModelPoints - 1)) {
+    st.winner = h;
+    st.max_good = g;
+    st.best_mask = mask;
+    st.niters = update_num_iters(confidence, (double)(n - g) / n, st.niters);
   }
 }
 
-// cv2's acceptance loop over one segment of consecutive hypotheses held one per lane (mk = inlier mask of hypothesis h;
-// lanes of the segment = seg_bits).  Every lane of the warp must call this (different segments may belong to
-// different frames); `live` = the lane's segment belongs to a frame.
-__device__ __forceinline__ void accept_segment(unsigned mk, int h, bool live, unsigned seg_bits, int lane, int n, double confidence, ReplayState& st) {
-  const int g = __popc(mk);
-  int consumed = -1;  // lanes up to here have been walked
-  for (;;) {
-    const bool c = live && lane > consumed && h < st.niters && g > max(st.max_good, kModelPoints - 1);
-    const unsigned cand = __ballot_sync(kFullMask, c) & seg_bits;
-    if (__all_sync(kFullMask, cand == 0u)) break;
-    const int first = cand ? __ffs(cand) - 1 : lane;
-    const int g1 = __shfl_sync(kFullMask, g, first);
-    const unsigned m1 = __shfl_sync(kFullMask, mk, first);
-    const int h1 = __shfl_sync(kFullMask, h, first);
-    if (cand) {
-      st.winner = h1;
-      st.max_good = g1;
-      st.best_mask = m1;
-      st.niters = update_num_iters(confidence, (double)(n - g1) / n, st.niters);
-      consumed = first;
-    }
-  }
-}
-
-// the frame has been walked up to hypothesis `end`: finished, or on to the next phase
-__device__ __forceinline__ void finish_or_continue(const RansacWorkspace& ws, int b, const ReplayState& st, int end, int iterations, int next_phase) {
+// the frame has been walked up to hypothesis `end`: finished, or on to phase `next_phase`
+__device__ __forceinline__ void finish_or_continue(const RansacWorkspace& ws, int b, ReplayState& st, int end, int iterations, int next_phase) {
   if (end >= st.niters || end >= iterations) {
     ws.x_winner[b] = st.winner;
     ws.x_mask[b] = st.best_mask;
     ws.x_visited[b] = st.niters;
   } else {
-    reinterpret_cast<ReplayState*>(ws.x_state)[b] = st;
+    st.next = end;
+    *state_of(ws, b) = st;
     const unsigned at = atomicAdd(ws.claim + kClaimActive + next_phase, 1u);
     ws.x_active[(size_t)(next_phase & 1) * ws.frames + at] = b;
   }
 }
 
-// Phase p: hypotheses [lo, lo + W) of every frame in the phase's work list (phase 0: of every frame).
-__global__ void __launch_bounds__(kReplayWarps * 32) replay_phase_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int p, int lo, int W) {
-  __shared__ FramePoints s_frames[kReplayWarps * 4];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ---- phase 0, step 1: per frame (one warp) — compact the visible landmarks once for all phases, walk the FP32 scores
+// with cv2's rule to predict how many hypotheses cv2's loop looks at, and append that many (frame, hypothesis) items.
+__global__ void __launch_bounds__(128) replay_plan_kernel(DevModel m, RansacArgs a, RansacWorkspace ws) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= a.B) return;
+  const int n = ws.n[b];
+  if (n <= kModelPoints) {  // no RANSAC for this frame: select_refit_kernel settles it
+    if (lane == 0) ws.x_winner[b] = -1, ws.x_mask[b] = 0u, ws.x_visited[b] = 0, ws.x_width[b] = 0;
+    return;
+  }
+  FramePoints& f = reinterpret_cast<FramePoints*>(ws.x_frames)[b];
+  const unsigned vis = ws.vis[b];
+  if (lane < n) {
+    const int j = __fns(vis, 0, lane + 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f.pw[lane][c] = (double)m.landmarks[3 * j + c];
+    const double2 q = ws.und[(size_t)b * m.J + j];
+    // hypotheses see the float32-rounded undistorted point (cv2 keeps the input dtype), App. B.3a
+    f.us[lane][0] = (double)(float)q.x * m.cam.fx + m.cam.cx;
+    f.us[lane][1] = (double)(float)q.y * m.cam.fy + m.cam.cy;
+    const float2 px = ws.img[(size_t)b * m.J + j];
+    f.img[lane][0] = px.x, f.img[lane][1] = px.y;
+    f.id[lane] = (uint8_t)j;
+  }
+  if (lane != 0) return;
+  int width = min(kPlanWidthNoScores, a.iterations);
+  if (a.H > 0) {
+    // cv2's loop over the FP32 counts of the first min(H, 32) draws: where would it stop?
+    const uint8_t* counts = ws.counts + (size_t)b * a.H;
+    const uint16_t* slot = m.slot + (size_t)(n - 6) * m.max_hyp;
+    int niters = a.iterations, max_good = 0, h = 0;
+    const int cap = min(min(a.H, kReplayPlanMax), a.iterations);
+    for (; h < cap && h < niters; ++h) {
+      const int g = counts[slot[h]];
+      if (g > max(max_good, kModelPoints - 1)) {
+        max_good = g;
+        niters = update_num_iters(a.confidence, (double)(n - g) / n, niters);
+      }
+    }
+    width = max(1, min(niters, cap));
+  }
+  ws.x_width[b] = width;
+  const unsigned at = atomicAdd(ws.claim + kClaimPlanItems, (unsigned)width);
+  for (int h = 0; h < width; ++h) ws.x_items[at + h] = ((uint32_t)b << 5) | (uint32_t)h;
+}
+
+// ---- phase 0, step 2: one thread per (frame, hypothesis) item
+__global__ void __launch_bounds__(kReplayWarps * 32, kReplayCtasPerSm) replay_eval_items_kernel(DevModel m, RansacArgs a, RansacWorkspace ws) {
+  const unsigned total = ws.claim[kClaimPlanItems];
   const float thr2 = a.reproj_err * a.reproj_err;
-  const int L = W < 32 ? W : 32;             // lanes (hypotheses) per frame and block
-  const int F = 32 / L;                      // frames per warp item
-  const int nb = W / L;                      // blocks per frame
-  const int sub = lane % L, grp = lane / L;  // lane within the frame's segment, segment within the warp
-  const unsigned seg_bits = (L == 32 ? kFullMask : ((1u << L) - 1u)) << (grp * L);
-  FramePoints& f = s_frames[warp * 4 + grp];
-  const int n_frames = p == 0 ? a.B : (int)ws.claim[kClaimActive + p];
-  const long long items = p == 0 ? (n_frames + F - 1) / F : (long long)n_frames * nb;
-  const int32_t* active = ws.x_active + (size_t)(p & 1) * ws.frames;
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t item = ws.x_items[i];
+    const int b = (int)(item >> 5), h = (int)(item & 31u);
+    const int n = ws.n[b];
+    const uint8_t* subset = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
+    ws.x_masks[(size_t)b * kReplayMaxWidth + h] = hypothesis_f64(m.cam, frame_of(ws, b), n, subset, thr2);
+  }
+}
+
+// ---- phase 0, step 3: per frame, cv2's loop over the evaluated prefix
+__global__ void __launch_bounds__(128) replay_scan_items_kernel(RansacArgs a, RansacWorkspace ws) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= a.B) return;
+  const int n = ws.n[b];
+  if (n <= kModelPoints) return;
+  const int width = ws.x_width[b];
+  ReplayState st{a.iterations, 0, -1, 0u, 0, {0, 0, 0}};
+  const uint32_t* masks = ws.x_masks + (size_t)b * kReplayMaxWidth;
+  for (int h = 0; h < width && h < st.niters; ++h) accept(st, h, masks[h], n, a.confidence);
+  finish_or_continue(ws, b, st, width, a.iterations, 1);
+}
+
+// cv2's acceptance loop over 32 consecutive hypotheses held one per lane (mk = inlier mask of hypothesis h); the state is
+// replicated on the lanes.  Every lane of the warp must call this.
+__device__ __forceinline__ void accept_block(unsigned mk, int h, int lane, int n, double confidence, ReplayState& st) {
+  const int g = __popc(mk);
+  int consumed = -1;  // lanes up to here have been walked
   for (;;) {
-    long long item = 0;
-    if (lane == 0) item = (long long)atomicAdd(ws.claim + kClaimItem + p, 1u);
-    item = __shfl_sync(kFullMask, item, 0);
-    if (item >= items) break;
-    // which frame, which block
-    int b = -1, blk = 0, row = 0;
-    if (p == 0) {
-      row = (int)item * F + grp;
-      b = row < n_frames ? row : -1;
-    } else {
-      row = (int)(item / nb);
-      blk = (int)(item - (long long)row * nb);
-      b = active[row];
-    }
-    int n = b >= 0 ? ws.n[b] : 0;
-    ReplayState st{a.iterations, 0, -1, 0u};
-    if (b >= 0 && n <= kModelPoints) {  // no RANSAC for this frame: select_refit_kernel settles it
-      if (sub == 0) ws.x_winner[b] = -1, ws.x_mask[b] = 0u, ws.x_visited[b] = 0;
-      b = -1;
-    }
-    if (b >= 0 && p > 0) st = reinterpret_cast<const ReplayState*>(ws.x_state)[b];
-    __syncwarp();  // the previous item's readers are done with the warp's shared slots
-    if (b >= 0) load_frame(m, ws, b, n, f, sub, L);
-    __syncwarp();
-    const int h = lo + blk * L + sub;
+    const bool c = lane > consumed && h >= st.next && h < st.niters && g > max(st.max_good, kModelPoints - 1);
+    const unsigned cand = __ballot_sync(kFullMask, c);
+    if (cand == 0u) break;
+    const int first = __ffs(cand) - 1;
+    accept(st, __shfl_sync(kFullMask, h, first), __shfl_sync(kFullMask, mk, first), n, confidence);
+    consumed = first;
+  }
+}
+
+// ---- phase p >= 1: hypotheses [lo, lo + W) of every frame in the phase's work list, 32 per warp item
+__global__ void __launch_bounds__(kReplayWarps * 32, kReplayCtasPerSm) replay_phase_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int p, int lo, int W) {
+  const int lane = threadIdx.x & 31;
+  const float thr2 = a.reproj_err * a.reproj_err;
+  const int nb = W / 32;  // blocks per frame
+  const int n_frames = (int)ws.claim[kClaimActive + p];
+  const long long items = (long long)n_frames * nb;
+  const int32_t* active = ws.x_active + (size_t)(p & 1) * ws.frames;
+  const long long n_warps = (long long)gridDim.x * kReplayWarps;
+  for (long long item = (long long)blockIdx.x * kReplayWarps + (threadIdx.x >> 5); item < items; item += n_warps) {
+    const int row = (int)(item / nb), blk = (int)(item - (long long)row * nb);
+    const int b = active[row];
+    const int n = ws.n[b];
+    ReplayState st = *state_of(ws, b);
+    const int h = lo + blk * 32 + lane;
     unsigned bits = 0;
-    if (b >= 0 && h < st.niters && h < a.iterations) {
+    if (h >= st.next && h < st.niters && h < a.iterations) {
       const uint8_t* subset = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
-      bits = hypothesis_f64(m.cam, f, n, subset, thr2);
+      bits = hypothesis_f64(m.cam, frame_of(ws, b), n, subset, thr2);
     }
     if (nb == 1) {
       // the whole phase of this frame sits in the warp: walk it here
-      accept_segment(bits, h, b >= 0, seg_bits, lane, n, a.confidence, st);
-      if (b >= 0 && sub == 0) finish_or_continue(ws, b, st, lo + W, a.iterations, p + 1);
-    } else {
-      uint32_t* masks = ws.x_masks + (size_t)row * kReplayMaxWidth;
-      masks[blk * 32 + lane] = bits;
+      accept_block(bits, h, lane, n, a.confidence, st);
+      if (lane == 0) finish_or_continue(ws, b, st, lo + W, a.iterations, p + 1);
+      continue;
+    }
+    uint32_t* masks = ws.x_masks + (size_t)row * kReplayMaxWidth;
+    masks[blk * 32 + lane] = bits;
+    __threadfence();
+    unsigned done = 0;
+    if (lane == 0) done = atomicAdd(ws.x_done + b, 1u);
+    done = __shfl_sync(kFullMask, done, 0);
+    if (done == (unsigned)nb - 1u) {  // this warp completed the frame's last block: walk the whole phase in order
       __threadfence();
-      unsigned done = 0;
-      if (lane == 0) done = atomicAdd(ws.x_done + b, 1u);
-      done = __shfl_sync(kFullMask, done, 0);
-      if (done == (unsigned)nb - 1u) {  // this warp completed the frame's last block: walk the whole phase in order
-        __threadfence();
-        for (int c = 0; c < nb; ++c) {
-          const int hc = lo + c * 32 + lane;
-          const unsigned mk = __ldcg(masks + c * 32 + lane);
-          accept_segment(mk, hc, true, kFullMask, lane, n, a.confidence, st);
-          if (hc - lane + 32 >= st.niters) break;  // (uniform: st is replicated on the lanes)
-        }
-        if (lane == 0) {
-          ws.x_done[b] = 0u;
-          finish_or_continue(ws, b, st, lo + W, a.iterations, p + 1);
-        }
+      for (int c = 0; c < nb; ++c) {
+        const int hc = lo + c * 32 + lane;
+        if (hc - lane >= st.niters) break;  // (uniform: st is replicated on the lanes)
+        accept_block(__ldcg(masks + c * 32 + lane), hc, lane, n, a.confidence, st);
+      }
+      if (lane == 0) {
+        ws.x_done[b] = 0u;
+        finish_or_continue(ws, b, st, lo + W, a.iterations, p + 1);
       }
     }
   }
+}
+
+__global__ void replay_reset_kernel(RansacWorkspace ws, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < kClaimWords) ws.claim[i] = 0u;
+  if (i < B) ws.x_done[i] = 0u;
 }
 
 }  // namespace
 
 cudaError_t launch_ransac_replay(const Model& m, const RansacArgs& a, const RansacWorkspace& ws, cudaStream_t stream) {
   if (a.B == 0 || m.J <= kModelPoints) return cudaSuccess;
-  cudaError_t e = cudaMemsetAsync(ws.claim, 0, sizeof(uint32_t) * kClaimWords, stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(ws.x_done, 0, sizeof(uint32_t) * (size_t)a.B, stream);
-  if (e != cudaSuccess) return e;
   static PerDeviceOnce once;
-  e = once.run(m.device, [] { return cudaFuncSetAttribute(replay_phase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct); });
+  cudaError_t e = once.run(m.device, [] {
+    cudaError_t r = cudaFuncSetAttribute(replay_phase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    if (r == cudaSuccess) r = cudaFuncSetAttribute(replay_eval_items_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, kSmemCarveoutPct);
+    return r;
+  });
   if (e != cudaSuccess) return e;
   int dev = 0, num_sms = 0;
   e = current_device(dev, num_sms);
   if (e != cudaSuccess) return e;
   const DevModel dm = dev_model(m);
-  int lo = 0, W = kFirstWidth;
-  for (int p = 0; lo < a.iterations && p < kReplayMaxPhases; ++p) {
-    // persistent grid: two CTAs per SM at most; phase 0 never needs more warps than it has items
-    long long warps = p == 0 ? ((long long)a.B + 3) / 4 : (long long)2 * num_sms * kReplayWarps;
-    const int ctas = (int)std::max<long long>(1, std::min<long long>(2 * num_sms, (warps + kReplayWarps - 1) / kReplayWarps));
-    replay_phase_kernel<<<ctas, kReplayWarps * 32, 0, stream>>>(dm, a, ws, p, lo, W);
+  // counters and per-frame completion counts are reset by a kernel of the call itself (a memset node costs an engine
+  // switch of ~40 us between two kernels of a stream)
+  replay_reset_kernel<<<(std::max(a.B, kClaimWords) + 255) / 256, 256, 0, stream>>>(ws, a.B);
+  replay_plan_kernel<<<(a.B + 3) / 4, 128, 0, stream>>>(dm, a, ws);
+  // the item count lives on the device: a persistent grid sized for the most there can be
+  const long long max_items = (long long)a.B * (a.H > 0 ? kReplayPlanMax : kPlanWidthNoScores);
+  const int eval_ctas = (int)std::max<long long>(1, std::min<long long>(kReplayCtasPerSm * num_sms, (max_items + kReplayWarps * 32 - 1) / (kReplayWarps * 32)));
+  replay_eval_items_kernel<<<eval_ctas, kReplayWarps * 32, 0, stream>>>(dm, a, ws);
+  replay_scan_items_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, ws);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  // phase 1 starts at 0 again: a frame whose predicted prefix was shorter than cv2's real loop resumes at its own `next`
+  int lo = 0, W = 32;
+  for (int p = 1; lo < a.iterations && p < kReplayMaxPhases; ++p) {
+    replay_phase_kernel<<<kReplayCtasPerSm * num_sms, kReplayWarps * 32, 0, stream>>>(dm, a, ws, p, lo, W);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     lo += W;

@@ -21,12 +21,13 @@ namespace spe {
 
 constexpr int kExactEigIters = 10;  // inverse-iteration steps of the float64 eigen stage (block of four vectors)
 
-struct FramePoints {  // one frame's visible landmarks, compacted (shared memory, one per group)
+struct FramePoints {  // one frame's visible landmarks, compacted (workspace, written once per call by replay_plan_kernel)
   double pw[kMaxLandmarks][3];   // object points (the float32-rounded landmarks)
   double us[kMaxLandmarks][2];   // ideal pixel coordinates of the float32-rounded undistorted points (hypothesis input)
   float img[kMaxLandmarks][2];   // raw pixel coordinates (scoring)
   uint8_t id[kMaxLandmarks];     // landmark number of every compacted point
 };
+static_assert(sizeof(FramePoints) == kReplayFrameBytes, "FramePoints is carved as kReplayFrameBytes per frame");
 
 // EPnP on the five points `sub` (indices into the compacted frame, draw order) in float64, then the inlier mask of the
 // resulting pose over the frame's n points.  One thread, everything in registers / local memory.

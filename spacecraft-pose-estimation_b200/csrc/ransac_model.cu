@@ -227,7 +227,10 @@ RansacWorkspace carve_workspace(void* base, int J, int B, int H) {
   w.x_mask = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B));
   w.x_visited = static_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
   w.claim = static_cast<uint32_t*>(take(sizeof(uint32_t) * kClaimWords));
-  w.x_state = take(16 * (size_t)B);
+  w.x_state = take((size_t)kReplayStateBytes * B);
+  w.x_frames = take((size_t)kReplayFrameBytes * B);
+  w.x_width = static_cast<int32_t*>(take(sizeof(int32_t) * (size_t)B));
+  w.x_items = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B * kReplayPlanMax));
   w.x_done = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B));
   w.x_active = static_cast<int32_t*>(take(sizeof(int32_t) * 2 * (size_t)B));
   w.x_masks = static_cast<uint32_t*>(take(sizeof(uint32_t) * (size_t)B * kReplayMaxWidth));

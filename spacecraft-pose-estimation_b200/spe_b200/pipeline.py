@@ -210,20 +210,20 @@ class StreamedHeatmapToPose:
     """Software-pipelined executor for a STREAM of device-resident batches.
 
     The stage has a throughput-bound front (decode + FP32 hypothesis scoring) and a latency-bound tail (float64 replay
-    of cv2's loop, selection, float64 refit: ~0.3 ms whatever the batch size).  Submitting batch i+1's front on the
-    caller's stream while batch i's tail runs on a side stream hides the tail: spe_ransac_score_f32 /
-    spe_ransac_replay_f64 / spe_ransac_select_refit_f32 are the stages of the C ABI call.
+    of cv2's loop in a few dependent phases, selection, float64 refit: ~0.6 ms whatever the batch size, at low SM
+    occupancy).  Every slot has its own side stream: batch i's tail runs under the fronts of batches i+1 ... i+depth-1
+    on the caller's stream AND next to the tails of those batches.  spe_ransac_score_f32 / spe_ransac_replay_f64 /
+    spe_ransac_select_refit_f32 are the stages of the C ABI call.
     Results of a submit() are valid after wait(slot) or drain().  `depth` batches are in flight, each with its own
     workspace.  Outputs go to the slot's own tensors or to caller-provided ones (submit(..., out=StageOutput(...)), e.g.
     views of one [K*B,7] buffer that is all_gathered once at the end of the job).
     """
 
-    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 2, want_rt: bool = False, tail_priority: int = 0):
+    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 3, want_rt: bool = False, tail_priority: int = 0):
         torch = stage._torch
         self.stage, self.B, self.depth = stage, int(batch), int(depth)
         dev, J, H = stage.device, stage.solver.J, stage.hypotheses
         self._L = stage._L
-        self.side = torch.cuda.Stream(dev, priority=tail_priority)  # (priority makes no measurable difference)
         self.ws_bytes = int(self._L.spe_ransac_workspace_bytes(stage.solver.handle, self.B, H))
         self.slots = []
         cur = torch.cuda.current_stream(dev)
@@ -237,6 +237,7 @@ class StreamedHeatmapToPose:
                 "rt": torch.empty((self.B, 12), dtype=torch.float64, device=dev) if want_rt else None,
                 "ws": torch.empty(max(self.ws_bytes, 16), dtype=torch.uint8, device=dev),
                 "scored": torch.cuda.Event(), "done": done,
+                "side": torch.cuda.Stream(dev, priority=tail_priority),  # (priority makes no measurable difference)
             })
         self._next = 0
         self._pending = None
@@ -276,7 +277,7 @@ class StreamedHeatmapToPose:
         return slot
 
     def _enqueue_tail(self, slot):
-        st, side, out, ws = self.stage, self.side, slot["out"], slot["ws"]
+        st, side, out, ws = self.stage, slot["side"], slot["out"], slot["ws"]
         side.wait_event(slot["scored"])
         if st.exact:
             _lib.check(self._L.spe_ransac_replay_f64(st.solver.handle, self.B, st.hypotheses, st.reproj_err, st.confidence, ws.data_ptr(),

@@ -23,7 +23,10 @@ def main():
     ap.add_argument("--config", default="B")
     ap.add_argument("--landmarks", type=int, default=0)
     ap.add_argument("--pipelined", type=int, default=0, help="profile this many pipelined steps instead of one un-pipelined chunk")
+    ap.add_argument("--lib", default="", help="A/B runs: load this build of the library instead of spe_b200/libspe_b200.so")
     args = ap.parse_args()
+    if args.lib:
+        _lib.LIB_PATH = os.path.abspath(args.lib)
     cfg = dict(bench.CONFIGS[args.config])
     if args.config == "C" and args.landmarks:
         cfg["J"] = args.landmarks
