@@ -712,7 +712,12 @@ def main():
     ap.add_argument("--config", default="B", choices=sorted(CONFIGS))
     ap.add_argument("--landmarks", type=int, default=0, help="config C: 17 (events-config.yaml) or 24 (the shipped scripts' override)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--lib", default="", help="A/B runs only: load this build of the library (tools/ab_builds.py) instead of the shipped one")
     args = ap.parse_args()
+    if args.lib:
+        from spe_b200 import _lib as _spe_lib
+
+        _spe_lib.LIB_PATH = os.path.abspath(args.lib)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -723,7 +728,8 @@ def main():
         # launched without torchrun: re-launch one process per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                "--master-port", str(29500 + os.getpid() % 2000), os.path.abspath(__file__), "--gpus", str(args.gpus), "--steps", str(args.steps),
-               "--warmup", str(args.warmup), "--repeats", str(args.repeats), "--config", args.config, "--landmarks", str(args.landmarks)]
+               "--warmup", str(args.warmup), "--repeats", str(args.repeats), "--config", args.config, "--landmarks", str(args.landmarks)] + (
+                   ["--lib", args.lib] if args.lib else [])
         raise SystemExit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     gpu_arm(args, rank, local_rank, world)
 

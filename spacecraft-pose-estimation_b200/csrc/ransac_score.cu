@@ -115,7 +115,7 @@ constexpr int kT1Stride = 4 * 12 + 20 + 1;  // per-thread scratch: v[4][12], alp
 // shared memory of one warp: landmarks [32][3], ideal + raw pixels [32] float2 each, per-thread scratch
 constexpr int kT1WarpBytes = (int)(sizeof(float) * 3 * kMaxLandmarks + 2 * sizeof(float2) * kMaxLandmarks + sizeof(float) * 32 * kT1Stride +
                                    kMaxLandmarks /* landmark id of every compacted point */);
-constexpr int kT1MaxWarps = 12;  // 12 x 168 registers x 32 = one SM's register file
+constexpr int kT1MaxWarps = 65536 / (32 * ((SPE_T1_REGS + 7) / 8 * 8));  // one CTA = one SM's register file: 12 warps x 168 registers
 static_assert(kT1WarpBytes % 16 == 0, "per-warp shared-memory slice must stay 16-byte aligned");
 
 template <int kEig>  // 0: Householder QR + inverse iteration (default), 1: one-sided Jacobi SVD of M^T

@@ -18,6 +18,7 @@ for c in B A C D; do
   timeout 900 python bench.py --config $c --steps 20 --warmup 3 > $OUT/bench_${c}_n1_$TAG.json 2> $OUT/bench_${c}_n1.err
 done
 timeout 900 python bench.py --config C --landmarks 24 --steps 20 --warmup 3 > $OUT/bench_C24_n1_$TAG.json 2> $OUT/bench_C24_n1.err
+timeout 900 python bench.py --config E > $OUT/bench_E_n1_$TAG.json 2> $OUT/bench_E_n1.err
 timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref.err
 
 # 3. launch list of three pipelined steps + of one un-pipelined chunk (per-launch times are cold-cache and serialised)
