@@ -17,6 +17,14 @@
 #define SPE_NOINLINE
 #endif
 
+// The small least-squares solves of the hypothesis evaluation (beta initialisations, Gauss-Newton steps) go through the
+// normal equations + Cholesky: in float64 the squared conditioning is harmless (agreement with cv2 identical to the
+// Householder version on every dataset of tests/test_exact_eval_host.py) and it costs ~40 % less.  The final refit
+// (ransac_refit.cu) keeps Householder QR.
+#ifndef SPE_EXACT_NORMAL_EQ
+#define SPE_EXACT_NORMAL_EQ true
+#endif
+
 namespace spe {
 
 constexpr int kExactEigIters = 10;  // inverse-iteration steps of the float64 eigen stage (block of four vectors)
@@ -98,7 +106,6 @@ SPE_HD SPE_NOINLINE unsigned hypothesis_f64(const Camera& cam, const FramePoints
     for (int i = 0; i < 48; ++i) dbg[i] = (&v[0][0])[i];
 #endif
   double L[6][10];
-  build_L<double>(v, L);
 #ifndef SPE_NO_NULL_BASIS_ROTATION
   // Canonical basis of the 2-D null space.  Any orthonormal (v0, v1) is a legal outcome of OpenCV's SVD (the two
   // singular values are exactly zero: its own basis is decided by rounding noise), but EPnP's initialisations are not
@@ -109,8 +116,19 @@ SPE_HD SPE_NOINLINE unsigned hypothesis_f64(const Camera& cam, const FramePoints
   // initialisation lands in the wrong basin on every frame), which a noise-chosen basis is not.
   {
     double A3[6][3], r6[6], b3[3];
+    {
+      constexpr int pa[6] = {0, 0, 0, 1, 1, 2}, pb[6] = {1, 2, 3, 2, 3, 3};
 #pragma unroll
-    for (int k = 0; k < 6; ++k) A3[k][0] = L[k][0], A3[k][1] = L[k][1], A3[k][2] = L[k][2], r6[k] = rho[k];
+      for (int k = 0; k < 6; ++k) {  // the three columns of L that involve v0 and v1 only
+        double d0[3], d1[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) d0[c] = v[0][3 * pa[k] + c] - v[0][3 * pb[k] + c], d1[c] = v[1][3 * pa[k] + c] - v[1][3 * pb[k] + c];
+        A3[k][0] = d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2];
+        A3[k][1] = 2.0 * (d0[0] * d1[0] + d0[1] * d1[1] + d0[2] * d1[2]);
+        A3[k][2] = d1[0] * d1[0] + d1[1] * d1[1] + d1[2] * d1[2];
+        r6[k] = rho[k];
+      }
+    }
     lsq_householder<double, 6, 3>(A3, r6, b3);
     // B = [[b0, b1/2], [b1/2, b2]]; Jacobi angle that diagonalises it, larger |eigenvalue| first
     const double off = 0.5 * b3[1], h = b3[2] - b3[0];
@@ -130,15 +148,15 @@ SPE_HD SPE_NOINLINE unsigned hypothesis_f64(const Camera& cam, const FramePoints
       v[0][i] = swap ? b : a;
       v[1][i] = swap ? -a : b;
     }
-    build_L<double>(v, L);
   }
 #endif
+  build_L<double>(v, L);
   double Rb[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, tb[3] = {0, 0, 0}, eb = 0.0;
 #pragma unroll 1
   for (int variant = 1; variant <= 3; ++variant) {
     double be[4];
-    approx_betas<double>(L, rho, variant, be);
-    gauss_newton<double>(L, rho, be);
+    approx_betas<double, SPE_EXACT_NORMAL_EQ>(L, rho, variant, be);
+    gauss_newton<double, SPE_EXACT_NORMAL_EQ>(L, rho, be);
     double ccs[4][3];
 #pragma unroll
     for (int j = 0; j < 4; ++j)

@@ -28,12 +28,15 @@ timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --cloc
   python tools/ncu_target.py --config B > /dev/null 2>&1
 
 # 4. ncu --set full of every kernel of one chunk, configs B and D (the counters bench.py quotes come from these)
+#    (the .ncu-rep files are ~45 MB each and gpurun brings back 64 MiB at most: keep the raw-metric CSV, drop the report)
 for c in B D; do
   timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -o $OUT/stage_$c python tools/ncu_target.py --config $c > $OUT/ncu_$c.log 2>&1
+  ncu -i $OUT/stage_$c.ncu-rep --page raw --csv > $OUT/stage_${c}_raw.csv 2>/dev/null
+  rm -f $OUT/stage_$c.ncu-rep
 done
 
 # 5. sanitizer pass over the smoke path
 timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_smoke.py > $OUT/sanitizer_memcheck.log 2>&1
 timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_smoke.py > $OUT/sanitizer_racecheck.log 2>&1
-tail -3 $OUT/sanitizer_*.log
+for f in $OUT/sanitizer_*.log; do echo "== $f"; tail -n 4 $f; done
 ls -la $OUT
