@@ -118,9 +118,14 @@ constexpr int kT1WarpBytes = (int)(sizeof(float) * 3 * kMaxLandmarks + 2 * sizeo
 constexpr int kT1MaxWarps = 65536 / (32 * ((SPE_T1_REGS + 7) / 8 * 8));  // one CTA = one SM's register file: 12 warps x 168 registers
 static_assert(kT1WarpBytes % 16 == 0, "per-warp shared-memory slice must stay 16-byte aligned");
 
+// U(n, h_begin) and U(n, h_end) for every point count (the distinct-set slots a launch covers), from the host tables
+struct UniqueRange {
+  uint16_t begin[kMaxLandmarks + 1], end[kMaxLandmarks + 1];
+};
+
 template <int kEig>  // 0: Householder QR + inverse iteration (default), 1: one-sided Jacobi SVD of M^T
 __global__ void __maxnreg__(SPE_T1_REGS)
-hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_begin, int h_end, int hblocks, const int32_t* __restrict__ need,
+hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_begin, int h_end, int hblocks, UniqueRange ur, const int32_t* __restrict__ need,
                      float thr2, int sweeps, RansacWorkspace ws) {
   // One warp = one work item: 32 consecutive DISTINCT minimal sets [u_begin + 32*hb, +32) of frame b, in the order of
   // their first draw (Model::d_uniq).  Warps of a CTA are independent (different frames in general), each with its own
@@ -143,10 +148,10 @@ hypothesis_kernel_t1(DevModel m, const float* __restrict__ kpts, int H, int h_be
   // the distinct sets first drawn in that range are the slots [U(n, h_begin), U(n, limit))
   const int limit = need ? min(need[b], h_end) : h_end;
   if (limit <= h_begin) return;
-  const int u_begin = h_begin > 0 ? unique_below(m, n, h_begin) : 0;
+  const int u_begin = ur.begin[n];  // = U(n, h_begin), computed on the host
   const int u = u_begin + hb * 32 + lane;
   if (u - lane >= limit) return;  // slot u draws at index >= u: nothing of this block lies below the limit
-  const int u_end = unique_below(m, n, limit);
+  const int u_end = need ? unique_below(m, n, limit) : (int)ur.end[n];  // a per-frame limit needs the search, a common one does not
   if (u - lane >= u_end) return;
   const unsigned vis = ws.vis[b];
   if (lane < n) {
@@ -553,7 +558,12 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
   // has in that range; warps whose frame has fewer (or a smaller adaptive budget) leave at once.
   auto launch = [&](int h_begin, int h_end, const int32_t* need) -> cudaError_t {
     int most = 0;
-    for (int n = kModelPoints + 1; n <= m.J; ++n) most = std::max(most, unique_sets(m, n, h_end) - unique_sets(m, n, h_begin));
+    UniqueRange ur{};
+    for (int n = kModelPoints + 1; n <= m.J; ++n) {
+      ur.begin[n] = (uint16_t)unique_sets(m, n, h_begin);
+      ur.end[n] = (uint16_t)unique_sets(m, n, h_end);
+      most = std::max(most, (int)ur.end[n] - (int)ur.begin[n]);
+    }
     const int hblocks = (most + 31) / 32;
     const long long items = (long long)a.B * hblocks;
     // small batches: spread the warps over the SMs instead of packing 12 of them into one CTA
@@ -564,11 +574,11 @@ cudaError_t launch_ransac_score(const Model& m, const RansacArgs& a, const Ransa
     if (ctas == 0) return cudaSuccess;
 #ifdef SPE_DEV
     if (a.kernel_variant == 2) {  // full SVD of M^T
-      hypothesis_kernel_t1<1><<<(unsigned)ctas, kWarps * 32, smem, stream>>>(dm, a.kpts, a.H, h_begin, h_end, hblocks, need, thr2, a.eig_iters, ws);
+      hypothesis_kernel_t1<1><<<(unsigned)ctas, kWarps * 32, smem, stream>>>(dm, a.kpts, a.H, h_begin, h_end, hblocks, ur, need, thr2, a.eig_iters, ws);
       return cudaGetLastError();
     }
 #endif
-    hypothesis_kernel_t1<0><<<(unsigned)ctas, kWarps * 32, smem, stream>>>(dm, a.kpts, a.H, h_begin, h_end, hblocks, need, thr2, a.eig_iters, ws);
+    hypothesis_kernel_t1<0><<<(unsigned)ctas, kWarps * 32, smem, stream>>>(dm, a.kpts, a.H, h_begin, h_end, hblocks, ur, need, thr2, a.eig_iters, ws);
     return cudaGetLastError();
   };
   if (a.adaptive && a.H > kFirstPass) {

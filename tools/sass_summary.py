@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "spacecraft-pose-estimation_b200", "spe_b200", "libspe_b200.so")
-WATCH = ["UBLKCP", "SYNCS", "REDUX", "CREDUX", "LDS", "LDG", "STG", "FFMA", "FMUL", "FADD", "MUFU", "DFMA", "DMUL", "DADD", "LDL", "STL", "ATOM", "RED", "SHFL", "VOTE",
+WATCH = ["UBLKCP", "SYNCS", "REDUX", "CREDUX", "LDS", "LDG", "STG", "FFMA", "FMUL", "FADD", "MUFU", "DFMA", "DMUL", "DADD", "LDL", "STL", "ATOMG", "REDG", "SHFL", "VOTE",
          "HMMA", "IMMA", "UTCHMMA", "UTCQMMA", "UTMALDG"]
 
 
