@@ -59,8 +59,9 @@ typedef enum spe_status {
 typedef enum spe_frame_status {
   SPE_FRAME_OK = 0,
   SPE_FRAME_TOO_FEW_POINTS = 1, /* n < 4: cv2.solvePnPRansac raises cv2.error */
-  SPE_FRAME_P3P_UNSUPPORTED = 2, /* n == 4: cv2 switches to its P3P kernel (out of scope) */
-  SPE_FRAME_NO_MODEL = 3         /* no hypothesis reached 5 inliers: cv2 returns ret = False */
+  SPE_FRAME_P3P_UNSUPPORTED = 2, /* (ABI 1; no longer produced: n == 4 is solved like cv2 does, with P3P on the four points) */
+  SPE_FRAME_NO_MODEL = 3         /* no hypothesis reached 5 inliers (cv2 returns ret = False), or n == 4 and the P3P has
+                                    no real solution (cv2 returns a NaN pose) */
 } spe_frame_status;
 
 typedef struct spe_model spe_model_t; /* opaque: landmarks, camera, per-n minimal-set tables */

@@ -17,6 +17,7 @@
 #include "device_util.cuh"
 #include "epnp_f64.cuh"
 #include "epnp_math.cuh"
+#include "p3p_f64.cuh"
 #include "ransac.cuh"
 #include "ransac_common.cuh"
 
@@ -571,6 +572,17 @@ __device__ void refine_lm_f64(int n, const double (*pw)[3], const double (*img)[
   }
 }
 
+// n == 4: cv2's P3P branch (p3p_f64.cuh), kept out of line so that the rare path costs the common one no registers
+__device__ __noinline__ bool p3p_four_points(const Camera& cam, const double (*pw)[3], const double (*und)[2], double (&R)[3][3], double (&t)[3]) {
+  double X[4][3], us[4][2];
+  for (int k = 0; k < 4; ++k) {
+    for (int c = 0; c < 3; ++c) X[k][c] = pw[k][c];
+    us[k][0] = und[k][0] * cam.fx + cam.cx;
+    us[k][1] = und[k][1] * cam.fy + cam.cy;
+  }
+  return solve_p3p_f64(cam, X, us, R, t);
+}
+
 // The kernel is serial-latency bound: its duration is the time ONE frame's dependent chain of
 // float64 instructions takes, whatever the batch size (spreading whole frames over more warps was
 // measured to buy nothing).  What shortens it is splitting a frame over lanes: every frame gets a
@@ -589,7 +601,8 @@ __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, Rans
   if (n < 4) {
     status = SPE_FRAME_TOO_FEW_POINTS;
   } else if (n == 4) {
-    status = SPE_FRAME_P3P_UNSUPPORTED;
+    inl = vis;  // cv2: four points -> solvePnP(SOLVEPNP_P3P) on them, no RANSAC, every point an inlier
+    winner = 0;
   } else if (n == kModelPoints) {
     inl = vis;  // cv2: model_points == npoints -> plain solvePnP, every point an inlier
     winner = 0;
@@ -630,13 +643,17 @@ __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, Rans
         const double2 q = ws.und[(size_t)b * m.J + j];
         // RANSAC's final solve converts the image points to float64 before undistorting; the
         // n == 5 shortcut hands cv2.solvePnP the float32 points, whose undistortion stays float32
-        und[k][0] = n == kModelPoints ? (double)(float)q.x : q.x;
-        und[k][1] = n == kModelPoints ? (double)(float)q.y : q.y;
+        und[k][0] = n <= kModelPoints ? (double)(float)q.x : q.x;
+        und[k][1] = n <= kModelPoints ? (double)(float)q.y : q.y;
         ++k;
       }
     extern __shared__ double s_mat[];  // [blockDim.x / 4][kFrameMatStride]
-    epnp_f64(k, pw, und, m.cam, R, t, sub, gmask, FrameMat12{s_mat + (threadIdx.x >> 2) * kFrameMatStride});
-    if (a.refine_lm) refine_lm_f64(k, pw, img, m.cam, R, t);
+    if (n == 4) {
+      if (!p3p_four_points(m.cam, pw, und, R, t)) status = SPE_FRAME_NO_MODEL;  // no real solution: cv2 returns garbage
+    } else {
+      epnp_f64(k, pw, und, m.cam, R, t, sub, gmask, FrameMat12{s_mat + (threadIdx.x >> 2) * kFrameMatStride});
+    }
+    if (a.refine_lm && status == SPE_FRAME_OK) refine_lm_f64(k, pw, img, m.cam, R, t);
   }
   if (sub != 0) return;
   double q[4] = {1, 0, 0, 0};
@@ -645,7 +662,7 @@ __global__ void __maxnreg__(SPE_REFIT_REGS) select_refit_kernel(DevModel m, Rans
   const bool ok = status == SPE_FRAME_OK;
   for (int i = 0; i < 4; ++i) o[i] = ok ? (float)q[i] : 0.f;
   for (int i = 0; i < 3; ++i) o[4 + i] = ok ? (float)t[i] : 0.f;
-  a.inlier_mask[b] = inl;
+  a.inlier_mask[b] = ok ? inl : 0u;
   a.status[b] = status;
   if (a.winner) a.winner[b] = winner;
   if (a.budget) a.budget[b] = budget;

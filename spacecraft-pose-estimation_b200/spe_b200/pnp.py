@@ -201,8 +201,7 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs=None, fla
     """cv2.solvePnPRansac's signature and return tuple for one frame, computed on the GPU.
 
     Returns (ret, rvec (3,1) float64, tvec (3,1) float64, inliers (k,1) int32 or None).
-    Raises ValueError for fewer than 4 points (cv2 raises cv2.error) and NotImplementedError for
-    exactly 4 points (cv2 switches to P3P).  `iterationsCount` is capped at 16384.  The result is cv2's loop replayed
+    Raises ValueError for fewer than 4 points (cv2 raises cv2.error); exactly 4 points take cv2's P3P branch.  `iterationsCount` is capped at 16384.  The result is cv2's loop replayed
     in float64 (exact=True, no FP32 scoring).
     """
     if flags != SOLVEPNP_EPNP:
@@ -214,8 +213,6 @@ def solvePnPRansac(objectPoints, imagePoints, cameraMatrix, distCoeffs=None, fla
         raise ValueError("objectPoints and imagePoints need the same number of points")
     if n < 4:
         raise ValueError("solvePnPRansac needs at least 4 points")
-    if n == 4:
-        raise NotImplementedError("n == 4 takes OpenCV's P3P kernel, which is out of scope")
     if n > 32:
         raise ValueError("at most 32 points per frame")
     H = int(min(max(iterationsCount, 1), _lib.MAX_HYPOTHESES))

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include "../../spacecraft-pose-estimation_b200/csrc/ransac_common.cuh"
+#include "../../spacecraft-pose-estimation_b200/csrc/p3p_f64.cuh"
 #include "../../spacecraft-pose-estimation_b200/csrc/ransac_exact_eval.cuh"
 
 extern "C" {
@@ -57,6 +58,30 @@ unsigned spe_host_hypothesis(const double* obj, const double* und, const float* 
     f.id[k] = (uint8_t)k;
   }
   return spe::hypothesis_f64(cam, f, n, subset, reproj_err * reproj_err, dbg);
+}
+
+// cv2's n == 4 branch: obj [4,3] (float32-rounded, as doubles), und [4,2] float64 undistorted normalised points (rounded to
+// float32 inside, as cv2 keeps the input dtype); Rt_out [12] = R row-major, then t.
+int spe_host_p3p(const double* obj, const double* und, const double* cam9, double* Rt_out) {
+  spe::Camera cam{cam9[0], cam9[1], cam9[2], cam9[3], cam9[4], cam9[5], cam9[6], cam9[7], cam9[8]};
+  double X[4][3], us[4][2], R[3][3], t[3];
+  for (int k = 0; k < 4; ++k) {
+    for (int c = 0; c < 3; ++c) X[k][c] = obj[3 * k + c];
+    us[k][0] = (double)(float)und[2 * k] * cam.fx + cam.cx;
+    us[k][1] = (double)(float)und[2 * k + 1] * cam.fy + cam.cy;
+  }
+  if (!spe::solve_p3p_f64(cam, X, us, R, t)) return 0;
+  for (int i = 0; i < 9; ++i) Rt_out[i] = R[i / 3][i % 3];
+  for (int i = 0; i < 3; ++i) Rt_out[9 + i] = t[i];
+  return 1;
+}
+
+int spe_host_quartic(const double* c5, double* roots4) {
+  double c[5], x[4];
+  for (int i = 0; i < 5; ++i) c[i] = c5[i];
+  const int n = spe::p3p::quartic_real_roots(c, x);
+  for (int i = 0; i < n; ++i) roots4[i] = x[i];
+  return n;
 }
 
 }  // extern "C"

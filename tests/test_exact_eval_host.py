@@ -22,7 +22,7 @@ OUT = os.path.join(HERE, "host", "exact_eval_host.so")
 @pytest.fixture(scope="module")
 def host_lib():
     csrc = os.path.join(os.path.dirname(HERE), "spacecraft-pose-estimation_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in ("ransac_exact_eval.cuh", "ransac_common.cuh", "epnp_math.cuh", "epnp_f64.cuh", "ransac.cuh")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in ("ransac_exact_eval.cuh", "ransac_common.cuh", "epnp_math.cuh", "epnp_f64.cuh", "p3p_f64.cuh", "ransac.cuh")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         cmd = ["nvcc", "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets", "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared",
                "-o", OUT, SRC]
@@ -83,3 +83,39 @@ def test_known_answer_frame(host_lib, pnp_golden):
     assert w == 2 and vis == 5
     assert mask == sum(1 << int(i) for i in g["e3_inliers"])
     assert [bin(int(x)).count("1") for x in hm[:5]] == [0, 0, 10, 10, 10]
+
+
+def test_host_build_of_the_p3p_branch_matches_cv2(host_lib):
+    """cv2's n == 4 branch (solvePnP with SOLVEPNP_P3P on the four points): csrc/p3p_f64.cuh compiled for the host."""
+    import cv2
+
+    import spe_b200
+    from oracle import epnp_ref, pnp_ref
+    from spe_b200 import synth
+
+    host_lib.spe_host_p3p.restype = ctypes.c_int
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    good = total = 0
+    for model in (spe_b200.models.tango(), spe_b200.models.hubble_synthetic(17)):
+        rng = np.random.default_rng(1)
+        B, J = 300, model.num_landmarks
+        rvec, tvec = synth.random_poses(rng, B, z_range=(2.0, 10.0))
+        pts = synth.project(model.landmarks, synth.rodrigues(rvec), tvec, model.K, model.dist) + rng.normal(scale=1.0, size=(B, J, 2))
+        cam = np.array([model.K[0, 0], model.K[1, 1], model.K[0, 2], model.K[1, 2], *model.dist[:5]])
+        for b in range(B):
+            idx = np.sort(rng.choice(J, 4, replace=False))
+            obj, img = model.landmarks[idx], pts[b, idx].astype(np.float32)
+            ok, rv, tv, inl = cv2.solvePnPRansac(obj, img, model.K, distCoeffs=model.dist, flags=cv2.SOLVEPNP_EPNP, iterationsCount=10000, reprojectionError=15.0)
+            if not (ok and np.all(np.isfinite(rv)) and np.all(np.isfinite(tv))):
+                continue  # cv2 reports NaN poses when the quartic has no real root
+            obj32 = np.ascontiguousarray(obj.astype(np.float32).astype(np.float64))
+            und = np.ascontiguousarray(epnp_ref.undistort_points(img.astype(np.float64), model.K, model.dist))
+            Rt = np.zeros(12)
+            total += 1
+            if not host_lib.spe_host_p3p(p(obj32), p(und), p(cam), p(Rt)):
+                continue
+            r = pnp_ref.rotation_angle_deg(Rt[:9].reshape(3, 3), cv2.Rodrigues(rv)[0])
+            t = np.linalg.norm(Rt[9:] - tv.ravel()) / np.linalg.norm(tv)
+            good += int(r <= 1e-3 and t <= 1e-4)
+    print(f"P3P branch (host build) within 1e-3 deg / 1e-4 of cv2 on {good}/{total} four-point frames")
+    assert total >= 550 and good >= 0.99 * total
