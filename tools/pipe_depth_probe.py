@@ -1,4 +1,4 @@
-"""Dev probe (profiles/step_r2.md): ms per pipelined 4096-frame step at config B for pipeline depths 1..4 and the three
+"""Dev probe (profiles/step_r2.md): ms per pipelined 4096-frame step at config B for pipeline depths 1..6 and the three
 selections (FP32 + float64 replay, replay only, FP32 only)."""
 import os
 import sys
@@ -17,10 +17,10 @@ cfg = bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "B"]
 frames = min(cfg["frames"], 4 * bench.CHUNK)
 for name, kw in (("fp32+replay", dict(exact=True)), ("replay only", dict(exact=True, hypotheses=0)), ("fp32 only", dict(exact=False))):
     row = []
-    for depth in (1, 2, 3, 4):
+    for depth in (1, 2, 3, 4, 5, 6):
         bench.PIPE_DEPTH = depth
         job = bench.Job(cfg, frames, 0, dev, **kw)
         ms, _, _, _ = bench.timed_regions(job, 20, 5, 1, dev, gather=False)
         row.append(float(np.median(ms)) / 20 / (frames // job.chunk))
         del job
-    print(f"{name:12s} ms per 4096-frame chunk at depth 1..4: " + "  ".join(f"{x:.4f}" for x in row), flush=True)
+    print(f"{name:12s} ms per 4096-frame chunk at depth 1..6: " + "  ".join(f"{x:.4f}" for x in row), flush=True)
