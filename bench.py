@@ -43,7 +43,7 @@ UNIT = "frames/s"
 REPROJ = 15.0
 ITERATIONS = 10000  # the reference's iterationsCount, export_predicted_poses_real.py:201
 CHUNK = 4096
-PIPE_DEPTH = 3  # chunks in flight: the float64 tail of a chunk (~0.6 ms of dependent phases) spans more than one front
+PIPE_DEPTH = 4  # chunks in flight: the float64 tail of a chunk (~0.6 ms of dependent phases) spans more than one front
 CONFIGS = {
     "A": dict(frames=64, scaling="weak", model="tango", J=11, hm=(64, 64), H=256,
               workload="Tango 11 landmarks, 64 frames of 64x64 heatmaps, 256 RANSAC-EPnP hypotheses (BASELINE.json configs[0])"),
@@ -338,7 +338,7 @@ class Job:
         self.chunk = min(CHUNK, frames_rank)
         self.hm, self.c, self.s = synth.device_heatmaps(self.model, frames_rank, cfg["hm"][0], cfg["hm"][1], seed=synth.BASE_SEED + 101 + rank, device=dev)
         self.pipe = StreamedHeatmapToPose(self.stage, self.chunk, depth=PIPE_DEPTH) if frames_rank % self.chunk == 0 else None
-        self.tailpipe = None
+        self.warm = False
         self.flush_buf = None
         if frames_rank * decode_bytes_per_frame(cfg) <= 2 * 126e6:  # small inputs would be served from the L2: flush it between steps
             self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -352,6 +352,9 @@ class Job:
 
     def run_steps(self, steps, out, decode_events=None):
         """Enqueue `steps` passes over the rank's frames; results go to out[k*frames : (k+1)*frames]."""
+        if not self.warm:  # every slot's plain run + graph capture happen here, never inside a timed region
+            self.pipe.warm_up(self.hm[:self.chunk], self.c[:self.chunk], self.s[:self.chunk])
+            self.warm = True
         from spe_b200.pipeline import StageOutput
 
         pipe, ch = self.pipe, self.chunk
@@ -497,6 +500,7 @@ def gpu_arm(args, rank, local_rank, world):
 
         j2.stage = HeatmapToPose(job.model, hypotheses=kw.get("hypotheses", H), reproj_err=REPROJ, device=dev, exact=kw["exact"], iterations=ITERATIONS)
         j2.pipe = StreamedHeatmapToPose(j2.stage, job.chunk, depth=PIPE_DEPTH)
+        j2.warm = False
         o2 = j2.outputs(steps)
         j2.run_steps(2, o2)
         m2, _, o2, _ = timed_regions(j2, steps, 3, world, dev, gather=True)
@@ -650,6 +654,7 @@ def sweep_arm(args, cfg, rank, world, dev, sampler):  # noqa: C901
                     pipe.submit(hm[lo:lo + ch], c[lo:lo + ch], s[lo:lo + ch], out=out)
                 pipe.drain()
 
+            pipe.warm_up(hm[:ch], c[:ch], s[:ch])
             run()
             reps = 5 if batch >= 65536 else 20
             ts = []

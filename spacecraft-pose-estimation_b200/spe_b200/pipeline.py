@@ -219,7 +219,7 @@ class StreamedHeatmapToPose:
     views of one [K*B,7] buffer that is all_gathered once at the end of the job).
     """
 
-    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 3, want_rt: bool = False, tail_priority: int = 0):
+    def __init__(self, stage: HeatmapToPose, batch: int, depth: int = 4, want_rt: bool = False, tail_priority: int = 0, graph_tail: bool = True):
         torch = stage._torch
         self.stage, self.B, self.depth = stage, int(batch), int(depth)
         dev, J, H = stage.device, stage.solver.J, stage.hypotheses
@@ -241,6 +241,12 @@ class StreamedHeatmapToPose:
             })
         self._next = 0
         self._pending = None
+        # graph_tail: a slot's tail is a chain of ~14 small dependent launches (replay phases, select/refit) with the same
+        # arguments every time (the slot's workspace and its own output tensors).  After one plain run it is captured into a
+        # CUDA graph and replayed with ONE launch per chunk: no host work between the phases, and eight ranks sharing a
+        # host no longer stretch the chain (measured at 8 GPUs per host, profiles/step_r2.md).  Caller-provided outputs are filled
+        # by three small copies behind the graph.
+        self.graph_tail = bool(graph_tail)
 
     def submit(self, hm, center, scale, out: StageOutput | None = None, decode_events=None):
         """Enqueue one batch on torch's CURRENT stream (the stream that produced hm / center / scale).  Returns the slot
@@ -276,9 +282,8 @@ class StreamedHeatmapToPose:
         self.flush()
         return slot
 
-    def _enqueue_tail(self, slot):
-        st, side, out, ws = self.stage, slot["side"], slot["out"], slot["ws"]
-        side.wait_event(slot["scored"])
+    def _tail_launches(self, slot, out, side):
+        st, ws = self.stage, slot["ws"]
         if st.exact:
             _lib.check(self._L.spe_ransac_replay_f64(st.solver.handle, self.B, st.hypotheses, st.reproj_err, st.confidence, ws.data_ptr(),
                                                      ws.numel(), side.cuda_stream), "spe_ransac_replay_f64")
@@ -286,12 +291,42 @@ class StreamedHeatmapToPose:
                                                        out.inlier_mask.data_ptr(), out.status.data_ptr(), None,
                                                        slot["rt"].data_ptr() if slot["rt"] is not None else None, ws.data_ptr(), ws.numel(),
                                                        st.flags | _lib.FLAG_BACKGROUND_TAIL, side.cuda_stream), "spe_ransac_select_refit_f32")
+
+    def _enqueue_tail(self, slot):
+        torch = self.stage._torch
+        side, out, own = slot["side"], slot["out"], slot["own"]
+        if self.graph_tail and slot.get("graph") is None and slot.get("plain_runs", 0) >= 1:
+            # capture once per slot, after a plain run has done every lazy one-time set-up (kernel attributes ...)
+            side.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                self._tail_launches(slot, own, side)
+            slot["graph"] = g
+        side.wait_event(slot["scored"])
+        if slot.get("graph") is not None:
+            with torch.cuda.stream(side):
+                slot["graph"].replay()
+                if out.pose7.data_ptr() != own.pose7.data_ptr():
+                    out.pose7.copy_(own.pose7, non_blocking=True)
+                    out.inlier_mask.copy_(own.inlier_mask, non_blocking=True)
+                    out.status.copy_(own.status, non_blocking=True)
+        else:
+            self._tail_launches(slot, out, side)
+            slot["plain_runs"] = slot.get("plain_runs", 0) + 1
         slot["done"].record(side)
         # outputs (and a caller-provided `out`) were allocated on other streams and are written here: tell the allocator
-        for t in (out.pose7, out.inlier_mask, out.status, out.kpts, ws, slot["rt"]):
+        for t in (out.pose7, out.inlier_mask, out.status, out.kpts, slot["ws"], slot["rt"]):
             if t is not None:
                 t.record_stream(side)
         self._pending = None
+
+    def warm_up(self, hm, center, scale):
+        """Run 2 x depth batches so that every slot has done its plain run and captured its tail graph (a capture
+        synchronises the device: keep it out of timed or latency-sensitive regions)."""
+        for _ in range(2 * self.depth):
+            self.submit(hm, center, scale)
+        self.drain()
+        self.stage._torch.cuda.current_stream(self.stage.device).synchronize()
 
     def flush(self):
         """Enqueue the tail of the most recent batch now."""
