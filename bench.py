@@ -58,8 +58,11 @@ CONFIGS = {
 }
 SWEEP_BATCHES = (1, 64, 1024, 4096, 65536, 1048576)
 SWEEP_HYPOTHESES = (64, 256, 1024, 2048)
-# sources whose change invalidates the ncu counters in profiles/ncu_counters.json
-KERNEL_SOURCES = ("csrc/decode.cu", "csrc/ransac_score.cu", "csrc/ransac_exact.cu", "csrc/ransac_refit.cu", "csrc/epnp_math.cuh", "csrc/epnp_f64.cuh")
+# sources whose change invalidates the ncu counters in profiles/ncu_counters.json, per quoted kernel
+KERNEL_SOURCES = {
+    "score": ("csrc/ransac_score.cu", "csrc/epnp_math.cuh", "csrc/ransac.cuh", "csrc/ransac_common.cuh", "csrc/device_util.cuh", "csrc/decode.cuh"),
+    "decode": ("csrc/decode.cu", "csrc/decode.cuh", "csrc/device_util.cuh"),
+}
 
 
 def metric_name(cfg):
@@ -75,25 +78,27 @@ def canonical_hyp_flops(cfg):
     return 126_400 + 54 * cfg["J"]  # SURVEY 8(d), canonical FP32 flops per hypothesis at n = J
 
 
-def kernel_source_hash():
+def kernel_source_hash(kernel):
     h = hashlib.sha1()
-    for rel in KERNEL_SOURCES:
+    for rel in KERNEL_SOURCES[kernel]:
         with open(os.path.join(PKG, rel), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
 
 
-def ncu_counters(config_key):
-    """ncu-derived per-launch counters (executed warp-instructions of the scoring kernels, DRAM traffic of the decode
-    kernel), written by tools/ncu_counters.py next to a hash of the kernel sources.  A stale or missing stamp returns
-    None: the bench then reports the time-based numbers only instead of quoting counters of another kernel."""
+def ncu_counters(config_key, kernel):
+    """ncu-derived per-launch counters of one quoted kernel ("score": executed warp-instructions of frame prep + the FP32
+    hypothesis kernel; "decode": DRAM traffic of the decode kernel), written by tools/ncu_counters.py next to a hash of
+    that kernel's sources.  A stale or missing stamp returns None: the bench then reports the time-based numbers only
+    instead of quoting counters of another kernel."""
     path = os.path.join(ROOT, "profiles", "ncu_counters.json")
     try:
         data = json.load(open(path))
     except Exception:
         return None, "profiles/ncu_counters.json missing"
-    if data.get("kernel_source_hash") != kernel_source_hash():
-        return None, f"profiles/ncu_counters.json is stale (captured at source hash {data.get('kernel_source_hash')}, now {kernel_source_hash()})"
+    have, now = (data.get("kernel_source_hashes") or {}).get(kernel), kernel_source_hash(kernel)
+    if have != now:
+        return None, f"profiles/ncu_counters.json is stale for the {kernel} kernel (captured at source hash {have}, now {now})"
     entry = data.get("configs", {}).get(config_key)
     if entry is None:
         return None, f"profiles/ncu_counters.json has no entry for config {config_key}"
@@ -565,7 +570,9 @@ def gpu_arm(args, rank, local_rank, world):
         alone_gbs = dbytes / (decode_alone_ms * 1e-3) / 1e9
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9  # G warp-instructions/s: one per scheduler per clock
-        counters, stale = ncu_counters(key if key != "C" else f"C{J}")
+        ckey = key if key != "C" else f"C{J}"
+        counters, stale = ncu_counters(ckey, "score")
+        dcounters, dstale = ncu_counters(ckey, "decode")
         dominant = {"bound": "issue", "kernel": "hypothesis_kernel_t1<0> (+ frame_prep_kernel) = spe_ransac_score_f32", "unit": "G warp-instructions/s",
                     "peak": issue_peak, "ms_per_launch": score_ms, "share_of_step": score_ms * (frames_rank // B) / (med / steps),
                     "note": "FP32 CUDA-core work with no dense contraction: the bound is the instruction issue rate (148 SMs x 4 schedulers x clock). "
@@ -600,8 +607,8 @@ def gpu_arm(args, rank, local_rank, world):
             "single_chunk_ms": {"frames": B, "decode": decode_alone_ms, "score_fp32": score_ms, "replay_f64": replay_ms, "select_refit_f64": refit_ms,
                                 "total": decode_alone_ms + score_ms + replay_ms + refit_ms, "cv2_hypotheses_looked_at_per_frame": visited_mean},
             "roofline": {"bound": "hbm", "kernel": "decode_dyn_kernel", "achieved": decode_gbs, "peak": hbm_sustained, "unit": "GB/s",
-                         "frac": decode_gbs / hbm_sustained, "traffic": (counters or {}).get("decode_dram_bytes_per_launch"),
-                         "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_counters.json)" if counters else stale,
+                         "frac": decode_gbs / hbm_sustained, "traffic": (dcounters or {}).get("decode_dram_bytes_per_launch"),
+                         "traffic_note": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch (profiles/ncu_counters.json)" if dcounters else dstale,
                          "peak_source": peak_src + " (sustained figure: the kernel is timed inside a long step)", "ms_per_launch": decode_ms,
                          "algorithmic_bytes_per_launch": dbytes,
                          "note": "ms_per_launch is measured inside the timed, software-pipelined region, where the decode shares the chip with the previous "

@@ -350,6 +350,7 @@ hypothesis_kernel(DevModel m, const float* __restrict__ kpts, int H, int hblocks
     ws.masks[(size_t)b * H + h] = bits;
     ws.counts[(size_t)b * H + h] = (uint8_t)__popc(bits);
   }
+}
 
 // One Jacobi rotation between the columns at register positions P and Q of A, with the two
 // columns SWAPPED on output.  With the swap built in, the odd-even ordering below brings every

@@ -54,7 +54,10 @@ namespace {
 #ifndef SPE_REPLAY_CTAS_PER_SM
 #define SPE_REPLAY_CTAS_PER_SM 2  // 128 threads x 255 registers: two CTAs per SM (A/B: tools/ab_builds.py)
 #endif
-constexpr int kReplayWarps = 4;
+#ifndef SPE_REPLAY_WARPS
+#define SPE_REPLAY_WARPS 4
+#endif
+constexpr int kReplayWarps = SPE_REPLAY_WARPS;
 constexpr int kReplayCtasPerSm = SPE_REPLAY_CTAS_PER_SM;
 constexpr int kPlanWidthNoScores = 8;
 
@@ -182,31 +185,56 @@ __device__ __forceinline__ void accept_block(unsigned mk, int h, int lane, int n
   }
 }
 
-// ---- phase p >= 1: hypotheses [lo, lo + W) of every frame in the phase's work list, 32 per warp item
-__global__ void __launch_bounds__(kReplayWarps * 32, kReplayCtasPerSm) replay_phase_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int p, int lo, int W) {
+// U(n, lo) and U(n, lo + W) for every point count: the distinct minimal sets FIRST drawn in [lo, lo + W) are the slots
+// [begin[n], end[n]) of Model::d_uniq (host tables, ransac_model.cu)
+struct PhaseSets {
+  uint16_t begin[kMaxLandmarks + 1], end[kMaxLandmarks + 1];
+};
+
+// ---- phase p >= 1: hypotheses [lo, lo + W) of every frame in the phase's work list, 32 per warp item.
+// Phases wider than one warp (p >= 2) evaluate every DISTINCT minimal set once, at its first draw: a later draw of the
+// same five points (in whatever order) gives the same pose up to rounding, so its inlier count cannot be strictly
+// larger than the first one's and cv2's loop never accepts it.  OpenCV's RNG repeats itself heavily (n = 11: 462 sets
+// exist, the 10000 draws of a frame without a model contain each of them ~22 times), so a frame that stays in the loop
+// costs U(n, 10000) evaluations instead of 10000.  The first 32 draws (phase 0 / 1) are evaluated as drawn.
+__global__ void __launch_bounds__(kReplayWarps * 32, kReplayCtasPerSm) replay_phase_kernel(DevModel m, RansacArgs a, RansacWorkspace ws, int p, int lo, int W,
+                                                                                           PhaseSets sets) {
   const int lane = threadIdx.x & 31;
   const float thr2 = a.reproj_err * a.reproj_err;
-  const int nb = W / 32;  // blocks per frame
+  const int nb = W / 32;  // blocks per frame (upper bound: fewer when draws repeat earlier sets)
   const int n_frames = (int)ws.claim[kClaimActive + p];
   const long long items = (long long)n_frames * nb;
   const int32_t* active = ws.x_active + (size_t)(p & 1) * ws.frames;
   const long long n_warps = (long long)gridDim.x * kReplayWarps;
+  constexpr int kNever = 0x7fffffff;  // a lane without a hypothesis: beyond every budget
   for (long long item = (long long)blockIdx.x * kReplayWarps + (threadIdx.x >> 5); item < items; item += n_warps) {
     const int row = (int)(item / nb), blk = (int)(item - (long long)row * nb);
     const int b = active[row];
     const int n = ws.n[b];
-    ReplayState st = *state_of(ws, b);
-    const int h = lo + blk * 32 + lane;
-    unsigned bits = 0;
-    if (h >= st.next && h < st.niters && h < a.iterations) {
-      const uint8_t* subset = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
-      bits = hypothesis_f64(m.cam, frame_of(ws, b), n, subset, thr2);
-    }
     if (nb == 1) {
-      // the whole phase of this frame sits in the warp: walk it here
+      // the whole phase of this frame sits in the warp: evaluate the draws themselves and walk them here
+      ReplayState st = *state_of(ws, b);
+      const int h = lo + lane;
+      unsigned bits = 0;
+      if (h >= st.next && h < st.niters && h < a.iterations) {
+        const uint8_t* subset = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
+        bits = hypothesis_f64(m.cam, frame_of(ws, b), n, subset, thr2);
+      }
       accept_block(bits, h, lane, n, a.confidence, st);
       if (lane == 0) finish_or_continue(ws, b, st, lo + W, a.iterations, p + 1);
       continue;
+    }
+    const int u0 = sets.begin[n], u1 = sets.end[n];
+    const int nbf = max(1, (u1 - u0 + 31) >> 5);  // blocks this frame really has (>= 1: somebody has to walk it on)
+    if (blk >= nbf) continue;
+    const uint16_t* uniq = m.uniq + (size_t)(n - 6) * m.max_hyp;
+    ReplayState st = *state_of(ws, b);
+    const int u = u0 + blk * 32 + lane;
+    const int h = u < u1 ? (int)uniq[u] : kNever;  // the draw that introduces this set (ascending in u)
+    unsigned bits = 0;
+    if (h < st.niters) {  // (h >= lo >= st.next and h < iterations by construction)
+      const uint8_t* subset = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
+      bits = hypothesis_f64(m.cam, frame_of(ws, b), n, subset, thr2);
     }
     uint32_t* masks = ws.x_masks + (size_t)row * kReplayMaxWidth;
     masks[blk * 32 + lane] = bits;
@@ -214,11 +242,12 @@ __global__ void __launch_bounds__(kReplayWarps * 32, kReplayCtasPerSm) replay_ph
     unsigned done = 0;
     if (lane == 0) done = atomicAdd(ws.x_done + b, 1u);
     done = __shfl_sync(kFullMask, done, 0);
-    if (done == (unsigned)nb - 1u) {  // this warp completed the frame's last block: walk the whole phase in order
+    if (done == (unsigned)nbf - 1u) {  // this warp completed the frame's last block: walk the whole phase in order
       __threadfence();
-      for (int c = 0; c < nb; ++c) {
-        const int hc = lo + c * 32 + lane;
-        if (hc - lane >= st.niters) break;  // (uniform: st is replicated on the lanes)
+      for (int c = 0; c < nbf; ++c) {
+        const int uc = u0 + c * 32 + lane;
+        const int hc = uc < u1 ? (int)uniq[uc] : kNever;
+        if (__shfl_sync(kFullMask, hc, 0) >= st.niters) break;  // (uniform: st is replicated on the lanes, uniq ascends)
         accept_block(__ldcg(masks + c * 32 + lane), hc, lane, n, a.confidence, st);
       }
       if (lane == 0) {
@@ -264,7 +293,12 @@ cudaError_t launch_ransac_replay(const Model& m, const RansacArgs& a, const Rans
   // phase 1 starts at 0 again: a frame whose predicted prefix was shorter than cv2's real loop resumes at its own `next`
   int lo = 0, W = 32;
   for (int p = 1; lo < a.iterations && p < kReplayMaxPhases; ++p) {
-    replay_phase_kernel<<<kReplayCtasPerSm * num_sms, kReplayWarps * 32, 0, stream>>>(dm, a, ws, p, lo, W);
+    PhaseSets sets{};
+    for (int n = kModelPoints + 1; n <= m.J; ++n) {
+      sets.begin[n] = (uint16_t)unique_sets(m, n, lo);
+      sets.end[n] = (uint16_t)unique_sets(m, n, std::min(lo + W, a.iterations));
+    }
+    replay_phase_kernel<<<kReplayCtasPerSm * num_sms, kReplayWarps * 32, 0, stream>>>(dm, a, ws, p, lo, W, sets);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     lo += W;

@@ -691,7 +691,10 @@ cudaError_t launch_ransac_select_refit(const Model& m, const RansacArgs& a, cons
     return r;
   });
   if (ce != cudaSuccess) return ce;
-  int warps = a.refit_background ? kMaxTailWarps : 1;
+#ifndef SPE_TAIL_WARPS
+#define SPE_TAIL_WARPS kMaxTailWarps
+#endif
+  int warps = a.refit_background ? SPE_TAIL_WARPS : 1;
   if (a.tail_warps >= 1 && a.tail_warps <= kMaxTailWarps) warps = a.tail_warps;
   const int threads = 32 * warps;
   const int ctas = (a.B * 4 + threads - 1) / threads;

@@ -30,17 +30,22 @@ def test_stale_ncu_counters_are_refused(tmp_path, monkeypatch):
 
     monkeypatch.setattr(bench, "ROOT", str(tmp_path))
     os.makedirs(tmp_path / "profiles")
-    entry, why = bench.ncu_counters("B")
+    entry, why = bench.ncu_counters("B", "score")
     assert entry is None and "missing" in why
-    good = {"kernel_source_hash": bench.kernel_source_hash(), "commit": "abc1234", "configs": {"B": {"score_warp_instructions_per_launch": 1.0}}}
+    hashes = {k: bench.kernel_source_hash(k) for k in bench.KERNEL_SOURCES}
+    good = {"kernel_source_hashes": hashes, "commit": "abc1234", "configs": {"B": {"score_warp_instructions_per_launch": 1.0}}}
     (tmp_path / "profiles" / "ncu_counters.json").write_text(json.dumps(good))
-    entry, why = bench.ncu_counters("B")
-    assert why is None and entry["captured_at_commit"] == "abc1234"
-    entry, why = bench.ncu_counters("D")
+    for kernel in ("score", "decode"):
+        entry, why = bench.ncu_counters("B", kernel)
+        assert why is None and entry["captured_at_commit"] == "abc1234"
+    entry, why = bench.ncu_counters("D", "score")
     assert entry is None and "no entry" in why
-    (tmp_path / "profiles" / "ncu_counters.json").write_text(json.dumps(dict(good, kernel_source_hash="0" * 16)))
-    entry, why = bench.ncu_counters("B")
+    # each quoted kernel is stamped on its own: a change of the decode sources leaves the scoring counters valid
+    (tmp_path / "profiles" / "ncu_counters.json").write_text(json.dumps(dict(good, kernel_source_hashes=dict(hashes, decode="0" * 16))))
+    entry, why = bench.ncu_counters("B", "decode")
     assert entry is None and "stale" in why
+    entry, why = bench.ncu_counters("B", "score")
+    assert why is None
 
 
 def test_reference_arm_prints_one_contract_line():

@@ -74,3 +74,32 @@ def test_budget_beyond_the_scored_hypotheses_is_followed_to_cv2s_end():
     print(f"cv2 budgets: min {out.budget.min()}, median {int(np.median(out.budget))}, max {out.budget.max()}; "
           f"frames beyond 256 draws: {int(long_frames.sum())}/{B}")
     solver.close()
+
+
+def test_long_loops_over_repeated_minimal_sets_tango_11():
+    """11 Tango landmarks, 5-8 of them gross outliers: cv2's loop runs for 235 ... 10000 draws, of which only C(11,5) = 462
+    are distinct sets.  The replay evaluates a repeated set once (at its first draw) beyond the first 32 draws; the
+    outcome of cv2's loop — winner's inlier set, or no model at all — must not change."""
+    import spe_b200
+    from spe_b200 import synth
+
+    model = spe_b200.models.tango()
+    rng = np.random.default_rng(11)
+    B = 96
+    rvec, tvec = synth.random_poses(rng, B, z_range=(4.0, 10.0))
+    pts = synth.project(model.landmarks, synth.rodrigues(rvec), tvec, model.K, model.dist)
+    pts += rng.normal(scale=0.5, size=pts.shape)
+    for b in range(B):
+        bad = rng.choice(11, 5 + b % 4, replace=False)  # 8 outliers leave 3 good points: no model, all 10000 draws
+        pts[b, bad] = rng.uniform(0, 1920, (len(bad), 2)) if b % 2 else pts[b, bad] + rng.normal(scale=60.0, size=(len(bad), 2))
+    kpts = np.concatenate([pts, np.ones((B, 11, 1))], -1).astype(np.float32)
+    solver = spe_b200.PnPSolver(model.landmarks, model.K, model.dist, max_hypotheses=10000)
+    out = solver.solve(kpts, hypotheses=256, exact=True)
+    rep = population_parity("J=11, 5-8 outliers", model, kpts, out, iterations=10000)
+    assert_parity(rep, 0.9)
+    assert (out.budget > 672).sum() >= 8 and (out.status != 0).sum() >= 4, "the sample should reach the deep phases and contain frames without a model"
+    out0 = solver.solve(kpts, hypotheses=0, exact=True)
+    np.testing.assert_array_equal(out.inlier_mask, out0.inlier_mask)
+    np.testing.assert_array_equal(out.status, out0.status)
+    print(f"cv2 budgets: min {out.budget.min()}, median {int(np.median(out.budget))}, max {out.budget.max()}; no model: {(out.status != 0).sum()}/{B}")
+    solver.close()

@@ -55,9 +55,9 @@ def main():
     if '--summary' in sys.argv:
         summary_path = sys.argv[sys.argv.index('--summary') + 1]
     commit = subprocess.run(['git', '-C', ROOT, 'rev-parse', '--short', 'HEAD'], capture_output=True, text=True).stdout.strip()
-    data = {'kernel_source_hash': bench.kernel_source_hash(), 'commit': commit, 'configs': {}}
+    data = {'kernel_source_hashes': {k: bench.kernel_source_hash(k) for k in bench.KERNEL_SOURCES}, 'commit': commit, 'configs': {}}
     text = [f'# ncu --set full --clock-control none, one un-pipelined chunk per config (tools/ncu_target.py), commit {commit}, '
-            f'kernel-source hash {data["kernel_source_hash"]}', '']
+            f'kernel-source hashes {data["kernel_source_hashes"]}', '']
     for a in args:
         key, path = a.split('=', 1)
         hdr, units, rows = rows_of(path)
