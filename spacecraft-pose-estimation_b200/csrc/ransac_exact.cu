@@ -224,13 +224,21 @@ __global__ void __launch_bounds__(kReplayWarps * 32, kReplayCtasPerSm) replay_ph
       if (lane == 0) finish_or_continue(ws, b, st, lo + W, a.iterations, p + 1);
       continue;
     }
+#ifdef SPE_REPLAY_ALL_DRAWS  // A/B builds (tools/ab_builds.py): every draw evaluated, as before the distinct-set phases
+    const int u0 = lo, u1 = min(lo + W, a.iterations);
+#else
     const int u0 = sets.begin[n], u1 = sets.end[n];
+#endif
     const int nbf = max(1, (u1 - u0 + 31) >> 5);  // blocks this frame really has (>= 1: somebody has to walk it on)
     if (blk >= nbf) continue;
     const uint16_t* uniq = m.uniq + (size_t)(n - 6) * m.max_hyp;
     ReplayState st = *state_of(ws, b);
     const int u = u0 + blk * 32 + lane;
+#ifdef SPE_REPLAY_ALL_DRAWS
+    const int h = u < u1 ? u : kNever;
+#else
     const int h = u < u1 ? (int)uniq[u] : kNever;  // the draw that introduces this set (ascending in u)
+#endif
     unsigned bits = 0;
     if (h < st.niters) {  // (h >= lo >= st.next and h < iterations by construction)
       const uint8_t* subset = m.subsets + ((size_t)(n - 6) * m.max_hyp + h) * kModelPoints;
@@ -246,7 +254,11 @@ __global__ void __launch_bounds__(kReplayWarps * 32, kReplayCtasPerSm) replay_ph
       __threadfence();
       for (int c = 0; c < nbf; ++c) {
         const int uc = u0 + c * 32 + lane;
+#ifdef SPE_REPLAY_ALL_DRAWS
+        const int hc = uc < u1 ? uc : kNever;
+#else
         const int hc = uc < u1 ? (int)uniq[uc] : kNever;
+#endif
         if (__shfl_sync(kFullMask, hc, 0) >= st.niters) break;  // (uniform: st is replicated on the lanes, uniq ascends)
         accept_block(__ldcg(masks + c * 32 + lane), hc, lane, n, a.confidence, st);
       }

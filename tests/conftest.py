@@ -14,6 +14,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if os.environ.get("SPE_TEST_LIB"):  # A/B runs of the GPU tests against another build (tools/ab_builds.py); the product reads no environment
+        from spe_b200 import _lib
+
+        _lib.LIB_PATH = os.path.abspath(os.environ["SPE_TEST_LIB"])
 
 
 def pytest_collection_modifyitems(config, items):

@@ -16,6 +16,8 @@ for arg in sys.argv[1:] or ("128", "208"):
     if arg.startswith("replay"):  # replay3 / replay4: CTAs per SM of the float64 replay kernels (168 / 128 registers)
         n = int(arg[6:])
         print(mod.build(out=os.path.join(AB, f"libspe_replay{n}.so"), extra_flags=[f"-DSPE_REPLAY_CTAS_PER_SM={n}"]))
+    elif arg == "alldraws":  # the float64 replay evaluates every draw (no distinct-set phases)
+        print(mod.build(out=os.path.join(AB, "libspe_alldraws.so"), extra_flags=["-DSPE_REPLAY_ALL_DRAWS"]))
     elif arg.startswith("shape"):  # shape<RW>x<RC>t<TW>: replay kernels of RW warps x RC CTAs per SM, background refit CTAs of TW warps
         rw, rest = arg[5:].split("x")
         rc, tw = rest.split("t")
