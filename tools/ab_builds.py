@@ -16,6 +16,8 @@ for arg in sys.argv[1:] or ("128", "208"):
     if arg.startswith("replay"):  # replay3 / replay4: CTAs per SM of the float64 replay kernels (168 / 128 registers)
         n = int(arg[6:])
         print(mod.build(out=os.path.join(AB, f"libspe_replay{n}.so"), extra_flags=[f"-DSPE_REPLAY_CTAS_PER_SM={n}"]))
+    elif arg.startswith("refit"):  # refit168 / refit128: register budget of select_refit_kernel (12 / 16 warps per background CTA)
+        print(mod.build(out=os.path.join(AB, f"libspe_{arg}.so"), extra_flags=[f"-DSPE_REFIT_REGS={int(arg[5:])}"]))
     elif arg == "alldraws":  # the float64 replay evaluates every draw (no distinct-set phases)
         print(mod.build(out=os.path.join(AB, "libspe_alldraws.so"), extra_flags=["-DSPE_REPLAY_ALL_DRAWS"]))
     elif arg.startswith("shape"):  # shape<RW>x<RC>t<TW>: replay kernels of RW warps x RC CTAs per SM, background refit CTAs of TW warps
