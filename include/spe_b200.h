@@ -13,6 +13,8 @@
  *   spe_pick_boxes_f32 / spe_boxes_to_center_scale_f64
  *                            detection box choice + _xywh2cs (object_detection/export_object_detection_bounding_boxes.py
  *                            :313-329, landmark_regression/lib/dataset/PEdataset.py:98-113)
+ *   spe_pck_counts_f32       calc_dists + dist_acc behind accuracy()   landmark_regression/lib/core/evaluate.py:16-80
+ *                            (the other half of accuracy() is get_max_preds = spe_max_preds_f32)
  *   spe_heatmap_to_pose_f32  the two above back to back with no host hop (the reference goes
  *                            through pred.mat: lib/dataset/PEdataset.py:121-123 ->
  *                            export_predicted_poses_real.py:172-173)
@@ -135,6 +137,17 @@ int spe_boxes_to_center_scale_f64(const double* xywh, int B, float* center, floa
 int spe_pick_boxes_f32(const float* boxes, const float* scores, const int32_t* counts, int B, int K, double image_w,
                        double image_h, double* xywh, float* best_score, int32_t* best_index, float* center,
                        float* scale, void* stream);
+
+/* ---- accuracy() ------------------------------------------------------------------
+ * The counting half of core.evaluate.accuracy (landmark_regression/lib/core/evaluate.py:16-39: calc_dists, dist_acc) for
+ * the training / validation loops (lib/core/function.py:61-62, :395-396).  pred, target: [B,J,2] float32 argmax
+ * coordinates of the network output and of the target heatmaps (spe_max_preds_f32).  A (frame, joint) is counted when both
+ * target coordinates are > 1; its distance is |pred / norm - target / norm| in float64 with norm = (norm_x, norm_y) applied
+ * to (x, y) — the reference passes (H / 10, W / 10), in that order.  counts [J,2] int32 DEVICE (overwritten):
+ * per joint the number of counted frames and how many of them lie below `thr` (the reference: always 0.5, its own `thr`
+ * argument is not passed on, evaluate.py:71). */
+int spe_pck_counts_f32(const float* pred, const float* target, int B, int J, double norm_x, double norm_y, double thr,
+                       int32_t* counts, void* stream);
 
 /* ---- pose ---------------------------------------------------------------------------------
  * landmarks [J,3] float64 HOST (metres; rounded to float32 internally exactly like cv2 does),

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "spe_b200", "libspe_b200.so")
 OUT_DEV = os.path.join(HERE, "spe_b200", "libspe_b200_dev.so")
-SOURCES = ["decode.cu", "ransac_model.cu", "ransac_score.cu", "ransac_exact.cu", "ransac_refit.cu", "boxes.cu", "capi.cu"]
+SOURCES = ["decode.cu", "ransac_model.cu", "ransac_score.cu", "ransac_exact.cu", "ransac_refit.cu", "boxes.cu", "evaluate.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC",

@@ -4,6 +4,7 @@
 
 #include "../../include/spe_b200.h"
 #include "boxes.cuh"
+#include "evaluate.cuh"
 #include "decode.cuh"
 #include "ransac.cuh"
 
@@ -134,6 +135,14 @@ int spe_pick_boxes_f32(const float* boxes, const float* scores, const int32_t* c
   if (K == 0 && counts != nullptr) return SPE_ERR_INVALID_ARGUMENT;
   const cudaError_t e = spe::launch_pick_boxes(boxes, scores, counts, B, K, image_w, image_h, xywh, best_score, best_index, center, scale,
                                                static_cast<cudaStream_t>(stream));
+  return e == cudaSuccess ? SPE_OK : cuda_fail(e);
+}
+
+// ---- accuracy() ------------------------------------------------------------------------------
+int spe_pck_counts_f32(const float* pred, const float* target, int B, int J, double norm_x, double norm_y, double thr, int32_t* counts, void* stream) {
+  if (B < 0 || J <= 0 || !(norm_x > 0.0) || !(norm_y > 0.0) || counts == nullptr) return SPE_ERR_INVALID_ARGUMENT;
+  if (B > 0 && (pred == nullptr || target == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
+  const cudaError_t e = spe::launch_pck_counts(pred, target, B, J, norm_x, norm_y, thr, counts, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }
 

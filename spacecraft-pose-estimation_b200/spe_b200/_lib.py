@@ -54,6 +54,8 @@ def _declare(L):
     L.spe_boxes_to_center_scale_f64.argtypes = [dp, c_int, fp, fp, c_void_p]
     L.spe_pick_boxes_f32.restype = c_int
     L.spe_pick_boxes_f32.argtypes = [fp, fp, ip, c_int, c_int, c_double, c_double, dp, fp, ip, fp, fp, c_void_p]
+    L.spe_pck_counts_f32.restype = c_int
+    L.spe_pck_counts_f32.argtypes = [fp, fp, c_int, c_int, c_double, c_double, c_double, ip, c_void_p]
     if hasattr(L, "spe_pnp_model_create"):
         L.spe_pnp_model_create.restype = c_int
         L.spe_pnp_model_create.argtypes = [POINTER(c_double), c_int, POINTER(c_double), POINTER(c_double), c_int, POINTER(c_void_p)]
@@ -99,7 +101,7 @@ DECODE_BACKGROUND = 1
 
 EXPORTED_SYMBOLS = (
     "spe_abi_version", "spe_status_string", "spe_last_cuda_error", "spe_max_preds_f32", "spe_decode_f32",
-    "spe_decode_kpts_f32", "spe_decode_kpts_ex_f32", "spe_decode_combined_kpts_f32", "spe_boxes_to_center_scale_f64", "spe_pick_boxes_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
+    "spe_decode_kpts_f32", "spe_decode_kpts_ex_f32", "spe_decode_combined_kpts_f32", "spe_boxes_to_center_scale_f64", "spe_pick_boxes_f32", "spe_pck_counts_f32", "spe_pnp_model_create", "spe_pnp_model_destroy", "spe_pnp_model_num_landmarks",
     "spe_pnp_model_minimal_sets", "spe_pnp_minimal_sets_host", "spe_pnp_control_entry", "spe_ransac_replay_f64", "spe_ransac_read_budget", "spe_ransac_workspace_bytes", "spe_ransac_epnp_f32", "spe_ransac_score_f32",
     "spe_ransac_select_refit_f32", "spe_ransac_debug_scores",
     "spe_pipeline_workspace_bytes", "spe_heatmap_to_pose_f32",
