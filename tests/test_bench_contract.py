@@ -59,3 +59,22 @@ def test_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["config"] == "A" and d["config"]["hypotheses"] == 256 and d["gpu_launches"] == 0
+
+
+def test_static_bank_model_runs_on_the_shipped_library():
+    """tools/sass_bank_model.py (profiles/hyp_bank_r2.md): the FP32 hypothesis kernel's issue-rate ceiling from its operand reads."""
+    import shutil
+
+    lib = os.path.join(ROOT, "spacecraft-pose-estimation_b200", "spe_b200", "libspe_b200.so")
+    if shutil.which("cuobjdump") is None or not os.path.exists(lib):
+        import pytest
+
+        pytest.skip("needs cuobjdump and the built library")
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_bank_model.py"), lib, "hypothesis_kernel_t1", "--weights=6,5,4,11"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    import re
+
+    m = re.search(r"issue ceiling ([0-9.]+); at the measured ([0-9.]+) extra cycles -> ([0-9.]+)", res.stdout)
+    assert m, res.stdout
+    assert 0.6 < float(m.group(1)) < float(m.group(3)) < 0.9

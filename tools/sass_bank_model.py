@@ -5,9 +5,12 @@ registers it reads from the even bank, number from the odd bank); a source serve
 on the PREVIOUS instruction's same slot) does not count.  A three-source FFMA whose operands are all distinct therefore
 occupies the dispatch port for two cycles unless one of them is reused — the `dispatch_stall` ncu reports.
 
-    python tools/sass_bank_model.py <object or .so> <kernel substring> [--loops]
+    python tools/sass_bank_model.py <object or .so> <kernel substring> [--loops] [start:end:count ...] [--weights=c1,c2,...] [--penalty=0.6]
+    python tools/sass_bank_model.py spacecraft-pose-estimation_b200/spe_b200/libspe_b200.so hypothesis_kernel_t1 --weights=6,5,4,11
 
-Prints the FP32-arithmetic mix by dispatch cycles, weighted by the trip counts given with --trip start:end:count.
+Prints the FP32-arithmetic mix by dispatch cycles; loop bodies are weighted by trip counts given as hex address ranges
+or, with --weights, in address order of the loops longer than 64 instructions (hypothesis kernel: inverse iteration x 6,
+Gauss-Newton x 5, Procrustes sweeps x 4, scoring x 11 points).
 """
 import collections
 import re
@@ -96,6 +99,17 @@ def main():
             lo, hi, c = a.split(":")
             trips.append((int(lo, 16), int(hi, 16), float(c)))
     ins = parse(kernel_sass(path, name))
+    for a in sys.argv[3:]:
+        if a.startswith("--weights="):  # trip counts of the loops with more than 64 instructions, in address order
+            big = []
+            for addr, text in ins:
+                if "BRA" in text:
+                    m = re.findall(r"0x([0-9a-f]+)", text)
+                    if m and int(m[-1], 16) < addr and (addr - int(m[-1], 16)) // 16 > 64:
+                        big.append((int(m[-1], 16), addr))
+            counts = [float(x) for x in a.split("=")[1].split(",")]
+            assert len(counts) == len(big), f"{len(big)} loops found: {[(hex(x), hex(y)) for x, y in big]}"
+            trips += [(lo, hi, c) for (lo, hi), c in zip(big, counts)]
     if "--loops" in sys.argv:
         for addr, text in ins:
             if "BRA" in text:
