@@ -533,6 +533,20 @@ def gpu_arm(args, rank, local_rank, world):
             dist.barrier()
         torch.cuda.synchronize(dev)
         e2e_runs.append((time.perf_counter() - t0) * 1e3)
+    # the bound of the host-buffer call: the same pinned heatmaps copied to the device and nothing else (CUDA events)
+    h2d_dst = torch.empty_like(job.hm[:e2e_frames])
+    h2d_ms = []
+    for _ in range(4):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        c0.record(stream)
+        h2d_dst.copy_(hm_host, non_blocking=True)
+        c1.record(stream)
+        torch.cuda.synchronize(dev)
+        h2d_ms.append(c0.elapsed_time(c1))
+    h2d_gbs = hm_host.numel() * 4 / (min(h2d_ms[1:]) * 1e-3) / 1e9
+    del h2d_dst
     # parity spot check inside the bench: the host-call poses equal the device-call poses of the same frames
     same = bool((np.abs(hout.pose7 - pose_last[:e2e_frames].cpu().numpy()).max(axis=1) > 2e-6).mean() < 0.01)
     clocks = sampler.stop() if rank == 0 else None
@@ -601,7 +615,9 @@ def gpu_arm(args, rank, local_rank, world):
             "e2e": {"value": e2e_frames * world * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": e2e_frames * (J * HM_H * HM_W * 4 + 16),
                     "d2h_bytes_per_step": e2e_frames * (28 + 4 + 4 + J * 12), "frames_per_step": e2e_frames,
                     "api": "HeatmapToPose.run_host (pinned host tensors, 512-frame chunks, 2 streams), then the all_gather of the poses",
-                    "host_affinity": affinity},
+                    "host_affinity": affinity,
+                    "h2d_copy_gb_per_s_rank0": h2d_gbs, "frames_per_s_at_the_h2d_bound": world * h2d_gbs * 1e9 / (J * HM_H * HM_W * 4 + 16),
+                    "h2d_note": "pinned-memory copy of the same heatmaps alone (all ranks copying at once): the PCIe bound of a host-buffer caller"},
             "gpu_launches": job.launches_per_step() * steps,
             "step_issue": f"software-pipelined, {PIPE_DEPTH} chunks in flight (StreamedHeatmapToPose): the float64 replay + select/refit of a chunk run on the chunk's own side stream under the decode + FP32 scoring of the following chunks",
             "single_chunk_ms": {"frames": B, "decode": decode_alone_ms, "score_fp32": score_ms, "replay_f64": replay_ms, "select_refit_f64": refit_ms,
