@@ -592,6 +592,11 @@ def gpu_arm(args, rank, local_rank, world):
                     "note": "FP32 CUDA-core work with no dense contraction: the bound is the instruction issue rate (148 SMs x 4 schedulers x clock). "
                             "achieved = executed warp-instructions per launch (ncu smsp__inst_executed.sum, profiles/ncu_counters.json, stamped with the "
                             "kernel-source hash it was captured at) / the CUDA-event time measured here",
+                    "share_note": "share_of_step is taken against the software-pipelined step, in which the float64 tail kernels run UNDER the fronts of "
+                                  "the following chunks.  ncu serialises launches: in profiles/launches_pipelined_r2.csv the latency-bound tail kernels "
+                                  "(a few SMs busy for one ~130 us evaluation per phase) count with their full duration and this kernel's share of the "
+                                  "serialised sum is 0.31; the two throughput-bound kernels keep their ratio (hypothesis : decode = 3.6 under ncu, 3.2 by "
+                                  "CUDA events here)",
                     "canonical_tflops": B * H * canonical_hyp_flops(cfg) / (score_ms * 1e-3) / 1e12,
                     "canonical_note": "SURVEY 8(d) work model of the reference algorithm at all H draws / time: not a utilisation (the kernel scores each distinct "
                                       "minimal set once and reaches EPnP's vectors with ~8x fewer operations than a 12x12 Jacobi)"}
