@@ -24,12 +24,14 @@ def main():
     ap.add_argument("--frames", type=int, default=2048)
     ap.add_argument("--whitebox", type=int, default=128)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "parity_r2.md"))
+    ap.add_argument("--seed-offset", type=int, default=0, help="another population of the same datasets (tests use 0)")
+    ap.add_argument("--exact-only", action="store_true", help="skip the FP32-only selection")
     args = ap.parse_args()
     try:
         commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or "n/a"
     except Exception:
         commit = "n/a"
-    lines = [f"# Pose parity over whole populations (commit {commit}, cv2 {__import__('cv2').__version__})", "",
+    lines = [f"# Pose parity over whole populations (commit {commit}, cv2 {__import__('cv2').__version__}, population seed offset {args.seed_offset})", "",
              f"{args.frames} frames per dataset, decoded by the oracle's get_final_preds; every frame with >= 6 visible landmarks compared with "
              "`cv2.solvePnPRansac(EPNP, iterationsCount=10000, reprojectionError=15)`.  Tolerance on frames with cv2's inlier set: 1e-3 deg / 1e-4 rel-t "
              "(float64 R|t).  A differing frame is *explained* when the independent float64 NumPy white box disagrees with cv2 there too, or cv2 changes "
@@ -39,10 +41,10 @@ def main():
     detail = []
     for name in DATASETS:
         t0 = time.time()
-        model, kpts = make_dataset(name, args.frames)
+        model, kpts = make_dataset(name, args.frames, seed_offset=args.seed_offset)
         H = DATASETS[name][4]
         solver = spe_b200.PnPSolver(model.landmarks, model.K, model.dist, max_hypotheses=10000)
-        for exact in (True, False):
+        for exact in ((True,) if args.exact_only else (True, False)):
             out = solver.solve(kpts, hypotheses=H, exact=exact)
             rep = population_parity(name, model, kpts, out, iterations=10000, whitebox_sample=args.whitebox if exact else 0)
             worst = max([d[2] for d in rep.disagree], default=0.0)
