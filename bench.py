@@ -377,7 +377,12 @@ class Job:
 
     def launches_per_step(self):
         n_chunks = self.frames // self.chunk
-        per_chunk = 1 + 1 + (1 if self.stage.hypotheses > 0 else 0) + (1 if self.stage.exact else 0) + 1  # decode, prep, scoring, replay, select/refit
+        per_chunk = 1 + 1 + (1 if self.stage.hypotheses > 0 else 0) + 1  # decode, frame prep, FP32 scoring, select/refit
+        if self.stage.exact:  # the float64 replay: reset, plan, phase-0 evaluation, scan, then one launch per phase (csrc/ransac_exact.cu)
+            per_chunk += 4
+            lo, width, p = 0, 32, 1
+            while lo < self.stage.iterations and p < 16:
+                per_chunk, lo, width, p = per_chunk + 1, lo + width, min(width * 4, 2048), p + 1
         return per_chunk * n_chunks
 
 
