@@ -7,7 +7,8 @@ set -u
 TAG=${1:-r2}
 OUT=gpurun_out/profiles_$TAG
 mkdir -p $OUT
-COMMIT=$(git rev-parse --short HEAD 2>/dev/null || echo "n/a")
+# the GPU box has no .git: pass the commit in, e.g.  gpurun -- "SPE_COMMIT=$(git rev-parse --short HEAD) bash tools/make_profiles.sh r2"
+COMMIT=${SPE_COMMIT:-$(git rev-parse --short HEAD 2>/dev/null || echo "n/a")}
 echo "commit $COMMIT, $(nvidia-smi --query-gpu=name,driver_version --format=csv,noheader | head -1), $(date -u +%FT%TZ)" > $OUT/STAMP.txt
 
 # 1. parity over whole populations (both selections), every differing frame listed

@@ -27,10 +27,12 @@ def main():
     ap.add_argument("--seed-offset", type=int, default=0, help="another population of the same datasets (tests use 0)")
     ap.add_argument("--exact-only", action="store_true", help="skip the FP32-only selection")
     args = ap.parse_args()
-    try:
-        commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or "n/a"
-    except Exception:
-        commit = "n/a"
+    commit = os.environ.get("SPE_COMMIT", "")
+    if not commit:
+        try:
+            commit = subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip() or "n/a"
+        except Exception:
+            commit = "n/a"
     lines = [f"# Pose parity over whole populations (commit {commit}, cv2 {__import__('cv2').__version__}, population seed offset {args.seed_offset})", "",
              f"{args.frames} frames per dataset, decoded by the oracle's get_final_preds; every frame with >= 6 visible landmarks compared with "
              "`cv2.solvePnPRansac(EPNP, iterationsCount=10000, reprojectionError=15)`.  Tolerance on frames with cv2's inlier set: 1e-3 deg / 1e-4 rel-t "
