@@ -142,6 +142,8 @@ int spe_pick_boxes_f32(const float* boxes, const float* scores, const int32_t* c
 int spe_pck_counts_f32(const float* pred, const float* target, int B, int J, double norm_x, double norm_y, double thr, int32_t* counts, void* stream) {
   if (B < 0 || J <= 0 || !(norm_x > 0.0) || !(norm_y > 0.0) || counts == nullptr) return SPE_ERR_INVALID_ARGUMENT;
   if (B > 0 && (pred == nullptr || target == nullptr)) return SPE_ERR_INVALID_ARGUMENT;
+  // the kernel reads (x, y) pairs as float2
+  if ((reinterpret_cast<uintptr_t>(pred) & 7u) || (reinterpret_cast<uintptr_t>(target) & 7u)) return SPE_ERR_INVALID_ARGUMENT;
   const cudaError_t e = spe::launch_pck_counts(pred, target, B, J, norm_x, norm_y, thr, counts, static_cast<cudaStream_t>(stream));
   return e == cudaSuccess ? SPE_OK : cuda_fail(e);
 }

@@ -98,6 +98,12 @@ def test_pose_entry_points_validate_arguments_without_gpu(lib):
     assert lib.spe_pnp_model_num_landmarks(None) == -1
     ptrs = (ctypes.c_void_p * 2)(None, None)
     assert lib.spe_decode_combined_kpts_f32(ptrs, 0, 0, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # K < 1
+    # accuracy(): null coordinates, no joints, a non-positive divisor, coordinates that are not float2-aligned
+    assert lib.spe_pck_counts_f32(None, None, 4, 11, 6.4, 6.4, 0.5, ctypes.c_void_p(16), None) == -1
+    assert lib.spe_pck_counts_f32(ctypes.c_void_p(16), ctypes.c_void_p(16), 4, 0, 6.4, 6.4, 0.5, ctypes.c_void_p(16), None) == -1
+    assert lib.spe_pck_counts_f32(ctypes.c_void_p(16), ctypes.c_void_p(16), 4, 11, 0.0, 6.4, 0.5, ctypes.c_void_p(16), None) == -1
+    assert lib.spe_pck_counts_f32(ctypes.c_void_p(20), ctypes.c_void_p(16), 4, 11, 6.4, 6.4, 0.5, ctypes.c_void_p(16), None) == -1
+    assert lib.spe_pck_counts_f32(ctypes.c_void_p(16), ctypes.c_void_p(16), 4, 11, 6.4, 6.4, 0.5, None, None) == -1
     assert lib.spe_decode_combined_kpts_f32(ptrs, 9, 0, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # K > 8
     assert lib.spe_decode_combined_kpts_f32(ptrs, 3, 1, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # flip needs K == 2
     assert lib.spe_decode_combined_kpts_f32(ptrs, 2, 7, None, 0, 4, 11, 64, 64, None, None, 1, None, None, None) == -1  # unknown mode
